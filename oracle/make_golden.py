@@ -1,0 +1,412 @@
+"""TEST INFRASTRUCTURE ONLY -- freeze outputs of the LIVE reference.
+
+Runs the unmodified reference (``/root/reference/src``, through
+``oracle/refshim.py``) in the builder container and writes small ``.npz``
+fixtures to ``tests/golden/``.  The reference's own tests hold no golden
+vectors for this path, so these files are the pin for
+both the C oracle and the CUDA engine.
+
+    python oracle/make_golden.py            # regenerate everything
+
+Every random input is drawn from a seeded numpy Generator; every random
+number the reference consumes *inside* its JIT code is re-drawn afterwards
+from Numba's own generator with the same seed and call sequence, so the
+fixtures also contain the exact uniforms / gaussians the reference used.
+"""
+import math
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import refshim  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+PI = math.pi
+
+# name -> Spec kwargs.  Covers: deep lattice / free / ideal / defects,
+# N even / odd / not a multiple of 4, N != L, non-integer L, near and far
+# Jastrow branches.
+SPECS = {
+    'deep_n100': dict(lattice_depth=100, lattice_ratio=1,
+                      interaction_strength=1, boson_number=100,
+                      supercell_size=100, tbf_contact_cutoff=25),
+    'll_n16': dict(lattice_depth=0, lattice_ratio=1, interaction_strength=4,
+                   boson_number=16, supercell_size=16, tbf_contact_cutoff=4),
+    'lat_n50': dict(lattice_depth=5 * PI ** 2, lattice_ratio=1,
+                    interaction_strength=2, boson_number=50,
+                    supercell_size=50, tbf_contact_cutoff=12.5),
+    'lat_n100': dict(lattice_depth=5 * PI ** 2, lattice_ratio=1,
+                     interaction_strength=2, boson_number=100,
+                     supercell_size=100, tbf_contact_cutoff=25),
+    'deep_n200': dict(lattice_depth=20 * PI ** 2, lattice_ratio=1,
+                      interaction_strength=2, boson_number=200,
+                      supercell_size=200, tbf_contact_cutoff=50),
+    'defects_n20': dict(lattice_depth=5 * PI ** 2, lattice_ratio=0.5,
+                        interaction_strength=3, boson_number=20,
+                        supercell_size=20, tbf_contact_cutoff=5,
+                        num_defects=4, defect_magnitude=2 * PI ** 2),
+    'ideal_n8': dict(lattice_depth=5 * PI ** 2, lattice_ratio=1,
+                     interaction_strength=0, boson_number=8,
+                     supercell_size=8, tbf_contact_cutoff=2),
+    'odd_n7': dict(lattice_depth=3 * PI ** 2, lattice_ratio=2.0,
+                   interaction_strength=1.5, boson_number=7,
+                   supercell_size=10, tbf_contact_cutoff=3.3),
+    'frac_n21': dict(lattice_depth=2 * PI ** 2, lattice_ratio=0.25,
+                     interaction_strength=8, boson_number=21,
+                     supercell_size=17.5, tbf_contact_cutoff=1.75),
+    'strong_n10': dict(lattice_depth=0, lattice_ratio=1,
+                       interaction_strength=200, boson_number=10,
+                       supercell_size=10, tbf_contact_cutoff=5),
+}
+
+
+def param_block(spec):
+    flat = [float(v) for part in (spec.params, spec.obf_params,
+                                  spec.tbf_params) for v in tuple(part)]
+    return np.array(flat, dtype=np.float64)
+
+
+def make_confs(rng, spec, nconf):
+    nop, size = spec.boson_number, spec.supercell_size
+    rm = abs(spec.tbf_contact_cutoff)
+    confs = np.zeros((nconf, 2, nop))
+    confs[:, 0, :] = rng.random((nconf, nop)) * size
+    # Row 1 (drift) is ignored by the model functions: fill with junk.
+    confs[:, 1, :] = rng.standard_normal((nconf, nop))
+    # Edge cases.
+    confs[0, 0, :] = np.linspace(0, size, nop, endpoint=False)   # regular
+    if nconf > 1 and nop >= 4:
+        c = confs[1, 0]
+        c[0] = 0.0                              # lower boundary
+        c[1] = np.nextafter(size, 0)            # just below L
+        c[2] = c[3] + 1e-9                      # nearly coincident pair
+    if nconf > 2 and nop >= 6:
+        c = confs[2, 0]
+        c[1] = (c[0] + rm) % size               # pair exactly at r_m
+        c[3] = (c[2] + 0.5 * size) % size       # pair at L/2
+        c[5] = size                             # recast quirk Q5: z == L
+    if nconf > 3 and nop >= 4:
+        c = confs[3, 0]
+        wa = spec.well_width
+        c[0] = 3 + wa                           # exactly on the well edge
+        c[1] = np.nextafter(3 + wa, 10)         # just inside the barrier
+        c[2] = 2.0                              # cell boundary
+    return confs
+
+
+def gen_model(mrbp, name, kwargs, rng):
+    model = mrbp.model
+    spec = model.Spec(**kwargs)
+    cf = model.core_funcs
+    nop = spec.boson_number
+    nconf = 4 if nop >= 200 else 12
+    confs = make_confs(rng, spec, nconf)
+    cfc = spec.cfc_spec
+    lnpsi = np.array([cf.wf_abs_log(c, *cfc) for c in confs])
+    energy = np.array([cf.energy(c, *cfc) for c in confs])
+    drift = np.array([cf.drift(c, *cfc)[1] for c in confs])
+    e_and_d = np.array([[cf.ith_energy_and_drift(i, c, *cfc)
+                         for i in range(nop)] for c in confs])
+    num_modes = min(2 * nop, 24)
+    momenta = np.arange(num_modes) * 2 * PI / spec.supercell_size
+    fdk = np.array([[cf.fourier_density(k, c, *cfc) for k in momenta]
+                    for c in confs])
+    ssf = np.stack([(fdk * fdk.conj()).real, fdk.real, fdk.imag], axis=-1)
+    out = dict(spec_keys=np.array(list(kwargs.keys())),
+               spec_vals=np.array([float(v) for v in kwargs.values()]),
+               params=param_block(spec), confs=confs, lnpsi=lnpsi,
+               energy=energy, drift=drift, ith_energy=e_and_d[..., 0],
+               ssf=ssf, num_modes=num_modes)
+    np.savez_compressed(os.path.join(GOLDEN, f'model_{name}.npz'), **out)
+    print(f'model_{name}: lnpsi[0]={lnpsi[0]:.15g} E[0]={energy[0]:.15g}')
+
+
+def numba_draws():
+    import numba as nb
+
+    @nb.njit
+    def draw_uniform(seed, n):
+        np.random.seed(seed)
+        out = np.empty(n)
+        for i in range(n):
+            out[i] = np.random.rand()
+        return out
+
+    @nb.njit
+    def draw_dmc(seed, counts_u, counts_n, nop):
+        """Replay the serial DMC call sequence: per step, counts_u[t] calls
+        of rand() (branching), then counts_n[t]*nop calls of normal()."""
+        np.random.seed(seed)
+        nts = counts_u.shape[0]
+        wmax_u = counts_u.max()
+        wmax_n = counts_n.max()
+        uni = np.zeros((nts, wmax_u))
+        nor = np.zeros((nts, wmax_n, nop))
+        for t in range(nts):
+            for s in range(counts_u[t]):
+                uni[t, s] = np.random.rand()
+            for s in range(counts_n[t]):
+                for i in range(nop):
+                    nor[t, s, i] = np.random.normal(0., 1.)
+        return uni, nor
+
+    return draw_uniform, draw_dmc
+
+
+def gen_dmc_step(mrbp, name, kwargs, rng):
+    """One bit-reproducible evolve_state call (sigma = 0), hand-made cloning
+    table with deaths and duplicates, poisoned `actual` energies (quirk Q1).
+    """
+    model, dmc = mrbp.model, mrbp.dmc
+    spec = model.Spec(**kwargs)
+    nop = spec.boson_number
+    wmax, n_ini = 24, 16
+    dt = 1e-3
+    sampling = dmc.Sampling(spec, dt, wmax, n_ini, rng_seed=1,
+                            jit_parallel=False)
+    cf = sampling.core_funcs
+    confs = np.zeros((n_ini, 2, nop))
+    confs[:, 0, :] = rng.random((n_ini, nop)) * spec.supercell_size
+    ini_state = sampling.build_state(confs)
+    cfc = sampling.cfc_spec
+    prev = cf.init_state_data_from_state(ini_state, cfc)
+    act = cf.init_state_data_from_state(ini_state, cfc)
+    nxt = cf.init_state_data_from_state(ini_state, cfc)
+    # Poison the persistent per-slot energies so Q1 is visible.
+    act.props.energy[:] = ini_state.props.energy + \
+        rng.standard_normal(wmax) * 3.0
+    act_energy_in = act.props.energy.copy()
+    bs = cf.init_branching_spec(wmax)
+    ref = np.array([0, 0, 1, 3, 3, 3, 4, 6, 7, 7, 8, 10, 11, 12, 13, 14, 15,
+                    15, 15, 2], dtype=np.int64)
+    nw = len(ref)
+    bs.cloning_ref[:nw] = ref
+    ref_energy = float(ini_state.ref_energy) + 0.37
+    cfc0 = cfc._replace(ddf_params=cfc.ddf_params._replace(sigma_spread=0.0))
+    cf.evolve_state(prev, act, nxt, nw, wmax, dt, ref_energy, bs, cfc0)
+    z_min, z_max = spec.boundaries
+    out = dict(params=param_block(spec), ini_confs=confs,
+               ini_state_confs=np.asarray(ini_state.confs),
+               ini_state_energy=np.asarray(ini_state.props.energy),
+               ini_state_weight=np.asarray(ini_state.props.weight),
+               ini_state_mask=np.asarray(ini_state.props.mask),
+               ini_ref_energy=float(ini_state.ref_energy),
+               ini_energy_sum=float(ini_state.energy),
+               act_energy_in=act_energy_in, cloning_ref=bs.cloning_ref.copy(),
+               num_walkers=nw, max_num_walkers=wmax, time_step=dt,
+               ref_energy=ref_energy, z_min=z_min, z_max=z_max,
+               act_confs=act.confs, act_energy=act.props.energy,
+               act_weight=act.props.weight, act_mask=act.props.mask,
+               next_confs=nxt.confs, next_energy=nxt.props.energy,
+               next_weight=nxt.props.weight)
+    np.savez_compressed(os.path.join(GOLDEN, f'dmc_step_{name}.npz'), **out)
+    print(f'dmc_step_{name}: next_w[:3]={nxt.props.weight[:3]}')
+
+
+def gen_branch(mrbp, rng, draw_uniform):
+    model, dmc = mrbp.model, mrbp.dmc
+    spec = model.Spec(**SPECS['ll_n16'])
+    cases = {}
+    for tag, (wprev, wmax, scale) in dict(
+            plain=(40, 64, 1.0), capped=(40, 44, 1.6),
+            dying=(40, 64, 0.3)).items():
+        sampling = dmc.Sampling(spec, 1e-3, wmax, wprev, rng_seed=1,
+                                jit_parallel=False)
+        cf = sampling.core_funcs
+        sd = cf.init_state_data((wmax,), sampling.cfc_spec)
+        w = np.exp(rng.standard_normal(wprev) * 0.5) * scale
+        sd.props.weight[:wprev] = w
+        bs = cf.init_branching_spec(wmax)
+        seed = 1234 + len(cases)
+        from phd_qmclib.qmc_base.utils import numba_seed
+        numba_seed(seed)
+        nw = cf.sync_branching_spec(sd, wprev, wmax, bs)
+        uni = draw_uniform(seed, wprev)
+        cases[tag] = dict(weights=w, uniforms=uni, wmax=wmax,
+                          num_walkers=nw, cloning_ref=bs.cloning_ref.copy())
+        print(f'branch_{tag}: W={nw}')
+    flat = {f'{t}_{k}': v for t, d in cases.items() for k, v in d.items()}
+    np.savez_compressed(os.path.join(GOLDEN, 'dmc_branch.npz'), **flat)
+
+
+def gen_dmc_blocks(mrbp, name, kwargs, rng, draw_dmc, *, n_ini, wmax, dt,
+                   nts, nblocks, num_modes, num_bins, pure, seed,
+                   nwc=0.125):
+    """The reference's own blocks() in serial mode with estimators, plus the
+    exact random numbers it consumed (replayed from Numba's generator)."""
+    model, dmc = mrbp.model, mrbp.dmc
+    spec = model.Spec(**kwargs)
+    nop = spec.boson_number
+    ssf_spec = dmc.SSFEstSpec(num_modes, as_pure_est=pure,
+                              pfw_num_time_steps=nts)
+    den_spec = dmc.DensityEstSpec(num_bins, as_pure_est=pure,
+                                  pfw_num_time_steps=nts)
+    sampling = dmc.Sampling(spec, dt, wmax, n_ini,
+                            num_walkers_control_factor=nwc, rng_seed=seed,
+                            density_est_spec=den_spec, ssf_est_spec=ssf_spec,
+                            jit_parallel=False)
+    confs = np.zeros((n_ini, 2, nop))
+    confs[:, 0, :] = rng.random((n_ini, nop)) * spec.supercell_size
+    ini_state = sampling.build_state(confs)
+    blocks = sampling.blocks(ini_state, nts, 0)
+    rec = dict(energy=[], weight=[], num_walkers=[], ref_energy=[],
+               accum_energy=[], density=[], ssf=[])
+    last = None
+    for b, block in zip(range(nblocks), blocks):
+        ip = block.iter_props
+        rec['energy'].append(ip.energy.copy())
+        rec['weight'].append(ip.weight.copy())
+        rec['num_walkers'].append(ip.num_walkers.copy())
+        rec['ref_energy'].append(ip.ref_energy.copy())
+        rec['accum_energy'].append(ip.accum_energy.copy())
+        rec['density'].append(block.iter_density.copy())
+        rec['ssf'].append(block.iter_ssf.copy())
+        last = block.last_state
+    nw = np.concatenate(rec['num_walkers']).astype(np.int64)
+    assert nw.max() < wmax, 'capacity hit: replay of the RNG would be wrong'
+    counts_u = np.concatenate([[n_ini], nw[:-1]]).astype(np.int64)
+    uni, nor = draw_dmc(seed, counts_u, nw, nop)
+    total = nts * nblocks
+    uniforms = np.zeros((total, wmax))
+    normals = np.zeros((total, wmax, nop))
+    uniforms[:, :uni.shape[1]] = uni
+    normals[:, :nor.shape[1]] = nor
+    z_min, z_max = spec.boundaries
+    out = dict(params=param_block(spec), ini_confs=confs, n_ini=n_ini,
+               max_num_walkers=wmax, time_step=dt, nts=nts, nblocks=nblocks,
+               nwc_factor=nwc, target_num_walkers=n_ini, z_min=z_min,
+               z_max=z_max, num_modes=num_modes, num_bins=num_bins,
+               pure=int(pure), uniforms=uniforms, normals=normals,
+               last_confs=np.asarray(last.confs),
+               last_energy=np.asarray(last.props.energy),
+               last_weight=np.asarray(last.props.weight),
+               last_mask=np.asarray(last.props.mask),
+               last_cloning_ref=np.asarray(last.branching_spec.cloning_ref),
+               last_num_walkers=int(last.num_walkers),
+               last_ref_energy=float(last.ref_energy),
+               last_accum_energy=float(last.accum_energy))
+    for k, v in rec.items():
+        out['it_' + k] = np.stack(v)
+    np.savez_compressed(os.path.join(GOLDEN, f'dmc_blocks_{name}.npz'), **out)
+    print(f'dmc_blocks_{name}: W={nw.tolist()} E_ref[-1]='
+          f'{out["it_ref_energy"][-1, -1]:.12g}')
+
+
+def gen_vmc_blocks(mrbp, name, kwargs, rng, draw_uniform, *, move_spread,
+                   ns, nblocks, num_modes, seed):
+    model, vmc = mrbp.model, mrbp.vmc
+    spec = model.Spec(**kwargs)
+    nop = spec.boson_number
+    sampling = vmc.Sampling(spec, move_spread, rng_seed=seed,
+                            ssf_est_spec=vmc.SSFEstSpec(num_modes))
+    conf = spec.get_sys_conf_buffer()
+    conf[0, :] = rng.random(nop) * spec.supercell_size
+    ini_conf = conf.copy()
+    ini_state = sampling.build_state(conf)
+    rec = dict(lnpsi=[], energy=[], stat=[], ssf=[], accept_rate=[])
+    last = None
+    for b, block in zip(range(nblocks), sampling.blocks(ns, ini_state)):
+        ip = block.iter_props
+        rec['lnpsi'].append(ip.wf_abs_log.copy())
+        rec['energy'].append(ip.energy.copy())
+        rec['stat'].append(ip.move_stat.copy())
+        rec['ssf'].append(block.iter_ssf.copy())
+        rec['accept_rate'].append(block.accept_rate)
+        last = block.last_state
+    total = ns * nblocks - 1          # first yield consumes no RNG
+    uni = draw_uniform(seed, total * (nop + 1)).reshape(total, nop + 1)
+    z_min, z_max = spec.boundaries
+    out = dict(params=param_block(spec), ini_conf=ini_conf,
+               ini_lnpsi=float(ini_state.wf_abs_log), move_spread=move_spread,
+               ns=ns, nblocks=nblocks, num_modes=num_modes, z_min=z_min,
+               z_max=z_max, uniforms=uni,
+               last_conf=np.asarray(last.sys_conf),
+               last_lnpsi=float(last.wf_abs_log))
+    for k, v in rec.items():
+        out['it_' + k] = np.stack(v)
+    np.savez_compressed(os.path.join(GOLDEN, f'vmc_blocks_{name}.npz'), **out)
+    print(f'vmc_blocks_{name}: accept={rec["accept_rate"]}')
+
+
+def gen_dmc_stat(mrbp, name, kwargs, *, n_target, wmax, dt, nts, nblocks,
+                 burn, seed, nwc=0.125):
+    """A longer serial reference DMC run: per-block sums for the
+    statistical parity test (reblocked error bars)."""
+    model, dmc = mrbp.model, mrbp.dmc
+    spec = model.Spec(**kwargs)
+    nop = spec.boson_number
+    sampling = dmc.Sampling(spec, dt, wmax, n_target,
+                            num_walkers_control_factor=nwc, rng_seed=seed,
+                            jit_parallel=False)
+    rng = np.random.default_rng(seed)
+    confs = np.zeros((n_target, 2, nop))
+    confs[:, 0, :] = rng.random((n_target, nop)) * spec.supercell_size
+    ini_state = sampling.build_state(confs)
+    e_sum, w_sum = [], []
+    for b, block in zip(range(burn + nblocks),
+                        sampling.blocks(ini_state, nts, burn)):
+        if b < burn:
+            continue
+        e_sum.append(block.iter_props.energy.sum())
+        w_sum.append(block.iter_props.weight.sum())
+    e_sum, w_sum = np.array(e_sum), np.array(w_sum)
+    out = dict(params=param_block(spec), ini_confs=confs, n_target=n_target,
+               max_num_walkers=wmax, time_step=dt, nts=nts, nblocks=nblocks,
+               burn=burn, nwc_factor=nwc, block_energy=e_sum,
+               block_weight=w_sum)
+    np.savez_compressed(os.path.join(GOLDEN, f'dmc_stat_{name}.npz'), **out)
+    epn = e_sum / w_sum / nop
+    print(f'dmc_stat_{name}: E/N = {epn.mean():.6f} +- '
+          f'{epn.std(ddof=1) / math.sqrt(len(epn)):.6f} (naive)')
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    which = set(sys.argv[1:]) or {'model', 'step', 'branch', 'blocks', 'vmc',
+                                  'stat'}
+    mrbp = refshim.load()
+    from phd_qmclib.mrbp_qmc import dmc, model, vmc  # noqa: F401
+    draw_uniform, draw_dmc = numba_draws()
+    if 'model' in which:
+        for i, (name, kw) in enumerate(SPECS.items()):
+            gen_model(mrbp, name, kw, np.random.default_rng(100 + i))
+    if 'step' in which:
+        for i, name in enumerate(['ll_n16', 'lat_n50', 'defects_n20',
+                                  'odd_n7']):
+            gen_dmc_step(mrbp, name, SPECS[name],
+                         np.random.default_rng(200 + i))
+    if 'branch' in which:
+        gen_branch(mrbp, np.random.default_rng(300), draw_uniform)
+    if 'blocks' in which:
+        gen_dmc_blocks(mrbp, 'll_n16', SPECS['ll_n16'],
+                       np.random.default_rng(400), draw_dmc, n_ini=24,
+                       wmax=40, dt=2e-3, nts=6, nblocks=2, num_modes=8,
+                       num_bins=32, pure=True, seed=11)
+        gen_dmc_blocks(mrbp, 'defects_n20_mixed', SPECS['defects_n20'],
+                       np.random.default_rng(401), draw_dmc, n_ini=12,
+                       wmax=24, dt=1e-3, nts=5, nblocks=2, num_modes=6,
+                       num_bins=40, pure=False, seed=12)
+    if 'vmc' in which:
+        gen_vmc_blocks(mrbp, 'll_n16', SPECS['ll_n16'],
+                       np.random.default_rng(500), draw_uniform,
+                       move_spread=0.25, ns=40, nblocks=2, num_modes=8,
+                       seed=5)
+        gen_vmc_blocks(mrbp, 'defects_n20', SPECS['defects_n20'],
+                       np.random.default_rng(501), draw_uniform,
+                       move_spread=0.25 * (1 / 1.5), ns=40, nblocks=2,
+                       num_modes=6, seed=6)
+    if 'stat' in which:
+        gen_dmc_stat(mrbp, 'll_n16', SPECS['ll_n16'], n_target=512, wmax=640,
+                     dt=2e-3, nts=256, nblocks=48, burn=12, seed=11)
+        gen_dmc_stat(mrbp, 'lat_n16', dict(
+            lattice_depth=5 * PI ** 2, lattice_ratio=1,
+            interaction_strength=2, boson_number=16, supercell_size=16,
+            tbf_contact_cutoff=4), n_target=512, wmax=640, dt=2e-3, nts=256,
+            nblocks=48, burn=12, seed=11)
+
+
+if __name__ == '__main__':
+    main()

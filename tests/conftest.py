@@ -1,0 +1,48 @@
+"""Shared fixtures.  `gpu` marks tests that need a B200 (run by the driver on
+the GPU box); everything else must pass on the CPU-only builder box."""
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+ORACLE_DIR = os.path.join(ROOT, 'oracle')
+if ORACLE_DIR not in sys.path:
+    sys.path.insert(0, ORACLE_DIR)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (B200)')
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def golden_names(prefix):
+    return sorted(os.path.basename(p)
+                  for p in glob.glob(os.path.join(GOLDEN, prefix + '*.npz')))
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+def maxnorm_err(a, b):
+    """Row-wise |a-b|_inf / |b|_inf (the drift criterion of SURVEY 8c)."""
+    a, b = np.atleast_2d(a), np.atleast_2d(b)
+    den = np.maximum(np.max(np.abs(b), axis=-1), 1e-300)
+    return float(np.max(np.max(np.abs(a - b), axis=-1) / den))
+
+
+@pytest.fixture(scope='session')
+def oracle():
+    import oracle as _o
+    _o.lib()
+    return _o
