@@ -59,7 +59,7 @@ SPECS = {
                      supercell_size=17.5, tbf_contact_cutoff=1.75),
     'strong_n10': dict(lattice_depth=0, lattice_ratio=1,
                        interaction_strength=200, boson_number=10,
-                       supercell_size=10, tbf_contact_cutoff=5),
+                       supercell_size=10, tbf_contact_cutoff=4.5),
 }
 
 
@@ -81,7 +81,7 @@ def make_confs(rng, spec, nconf):
     if nconf > 1 and nop >= 4:
         c = confs[1, 0]
         c[0] = 0.0                              # lower boundary
-        c[1] = np.nextafter(size, 0)            # just below L
+        c[1] = size * (1 - 2.0 ** -30)          # close pair across the wrap
         c[2] = c[3] + 1e-9                      # nearly coincident pair
     if nconf > 2 and nop >= 6:
         c = confs[2, 0]
@@ -92,7 +92,7 @@ def make_confs(rng, spec, nconf):
         c = confs[3, 0]
         wa = spec.well_width
         c[0] = 3 + wa                           # exactly on the well edge
-        c[1] = np.nextafter(3 + wa, 10)         # just inside the barrier
+        c[1] = 3 + wa + 1e-9                    # just inside the barrier
         c[2] = 2.0                              # cell boundary
     return confs
 

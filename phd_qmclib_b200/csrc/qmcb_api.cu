@@ -1,0 +1,808 @@
+// C ABI of libqmcb200.so (see include/qmcb200.h).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qmcb200.h"
+#include "qmcb_kernels.cuh"
+
+using namespace qmcb;
+
+namespace {
+
+std::string g_create_error;
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+};
+
+}  // namespace
+
+struct qmcb_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    qmcb_model_params params{};
+    DevModel M{};
+    GroupGeom geom{};
+    int sm_count = 0;
+    int max_smem = 0;
+    std::string err;
+
+    // scratch for host-pointer model evaluation
+    double *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+
+    // DMC
+    bool dmc_ready = false;
+    qmcb_dmc_params dp{};
+    DmcBufs B{};
+    DmcConsts C{};
+    DmcLog L{};
+    long long log_cap = 0;
+    long long step_host = 0;
+    int n_ini = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> step_ev;
+    bool profile_steps = false;
+    double last_total_ms = 0.0, last_step_ms = 0.0;
+    long long last_launches = 0;
+};
+
+#define CUDA_TRY(h, expr)                                                    \
+    do {                                                                     \
+        cudaError_t _e = (expr);                                             \
+        if (_e != cudaSuccess) {                                             \
+            char _b[512];                                                    \
+            snprintf(_b, sizeof _b, "%s failed at %s:%d: %s", #expr,         \
+                     __FILE__, __LINE__, cudaGetErrorString(_e));            \
+            (h)->err = _b;                                                   \
+            return QMCB_ERR_CUDA;                                            \
+        }                                                                    \
+    } while (0)
+
+#define FAIL(h, code, msg)                                                   \
+    do {                                                                     \
+        (h)->err = (msg);                                                    \
+        return (code);                                                       \
+    } while (0)
+
+namespace {
+
+// Host-side constants derived from the 25 reference scalars.
+bool build_model(const qmcb_model_params &p, DevModel &M, std::string &err)
+{
+    const double *m = p.model, *o = p.obf, *t = p.tbf;
+    double nopd = m[3];
+    if (!(nopd >= 1) || nopd != std::floor(nopd) || nopd > 4096) {
+        err = "boson_number must be an integer in [1, 4096]";
+        return false;
+    }
+    M.nop = (int) nopd;
+    M.nb = (M.nop + TB - 1) / TB;
+    M.kmax = M.nb / 2;
+    M.is_free = m[10] != 0.0;
+    M.is_ideal = m[11] != 0.0;
+    M.defects_sep = (int) m[7];
+    if (M.defects_sep < 1) M.defects_sep = 1;
+    M.L = m[4];
+    if (!(M.L > 0)) { err = "supercell_size must be positive"; return false; }
+    M.inv_L = 1.0 / M.L;
+    double v0 = o[0], r = o[1];
+    M.za = 1 / (1 + r);     // mrbp_qmc/model.py:420 recomputes it from r
+    M.zb = r / (1 + r);
+    M.e0 = o[4]; M.k1 = o[5]; M.kp1 = o[6];
+    M.v0 = v0;
+    M.vdef = m[6];
+    M.ln_cf = 0.0;
+    if (!M.is_free) {
+        double sh = std::sinh(0.5 * std::sqrt(v0 - M.e0) * M.zb);
+        M.ln_cf = 0.5 * std::log(1 + v0 / M.e0 * sh * sh);
+    }
+    double rm = std::fabs(t[1]);
+    double k2 = t[2], beta = t[3], r_off = t[4], am = t[5];
+    M.k2 = k2; M.beta = beta;
+    M.ln_am = std::log(std::fabs(am));
+    M.s_m = std::sin(M_PI * rm / M.L);
+    if (rm >= 0.5 * M.L) M.s_m = 1.0;
+    M.A_far = (M_PI / M.L) * beta;
+    M.B_far = (M_PI / M.L) * (M_PI / M.L) * beta;
+    M.A_near = -k2;
+    M.B_near = k2 * k2;
+    double phi = k2 * r_off;
+    M.cps0 = std::cos(phi); M.sps0 = std::sin(phi);
+    M.cps1 = std::cos(phi - k2 * M.L); M.sps1 = std::sin(phi - k2 * M.L);
+    return true;
+}
+
+// CTA shape: threads per walker = nb; pack G walkers into a CTA so that few
+// lanes idle, keeping >= ~10 resident warps per SM where shared memory and
+// registers allow.
+bool choose_geom(const DevModel &M, int max_smem, GroupGeom &g,
+                 std::string &err)
+{
+    const int regs_per_thread = 168;
+    double best = -1.0;
+    const int nbp = M.nb;
+    for (int nt = 64; nt <= 256; nt += 32) {
+        int G = nt / M.nb;
+        if (G < 1) continue;
+        int bytes = 0;
+        for (; G >= 1; --G) {
+            bytes = group_smem_doubles(G, nbp, M.kmax + 1) * 8;
+            if (bytes <= max_smem) break;
+        }
+        if (G < 1) continue;
+        double eff = (double) (G * M.nb) / nt;
+        int by_smem = (228 * 1024) / (bytes + 1024);
+        int by_regs = 65536 / (regs_per_thread * nt);
+        int by_thr = 2048 / nt;
+        int ctas = std::min(by_smem, std::min(by_regs, by_thr));
+        if (ctas < 1) ctas = 1;
+        double warps = ctas * nt / 32.0;
+        double score = eff * std::min(1.0, warps / 10.0);
+        if (score > best + 1e-9) {
+            best = score;
+            g.nthreads = nt; g.G = G; g.nbp = nbp; g.smem_bytes = bytes;
+        }
+    }
+    if (best < 0) {
+        err = "boson_number too large for the shared-memory pair tables "
+              "(limit ~440 particles)";
+        return false;
+    }
+    return true;
+}
+
+template <typename K>
+int set_smem(qmcb_handle *h, K kernel)
+{
+    CUDA_TRY(h, cudaFuncSetAttribute(
+                    kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                    h->geom.smem_bytes));
+    return QMCB_OK;
+}
+
+int ensure_scratch(qmcb_handle *h, size_t bytes)
+{
+    if (bytes <= h->scratch_bytes) return QMCB_OK;
+    if (h->d_scratch) CUDA_TRY(h, cudaFree(h->d_scratch));
+    h->d_scratch = nullptr;
+    h->scratch_bytes = 0;
+    CUDA_TRY(h, cudaMalloc(&h->d_scratch, bytes));
+    h->scratch_bytes = bytes;
+    return QMCB_OK;
+}
+
+int launch_model_eval(qmcb_handle *h, const EvalArgs &a, bool want_ln,
+                      bool want_ef)
+{
+    if (a.nconf <= 0) return QMCB_OK;
+    long long ctas = (a.nconf + h->geom.G - 1) / h->geom.G;
+    long long cap = (long long) h->sm_count * 32;
+    int grid = (int) std::min(ctas, cap);
+    dim3 blk(h->geom.nthreads);
+    size_t sm = h->geom.smem_bytes;
+    if (want_ln && want_ef)
+        model_eval_kernel<true, true><<<grid, blk, sm, h->stream>>>(
+            h->M, h->geom, a);
+    else if (want_ln)
+        model_eval_kernel<true, false><<<grid, blk, sm, h->stream>>>(
+            h->M, h->geom, a);
+    else
+        model_eval_kernel<false, true><<<grid, blk, sm, h->stream>>>(
+            h->M, h->geom, a);
+    CUDA_TRY(h, cudaGetLastError());
+    return QMCB_OK;
+}
+
+void free_dmc(qmcb_handle *h)
+{
+    DmcBufs &B = h->B;
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(B.confs[i]); cudaFree(B.energy[i]); cudaFree(B.weight[i]);
+    }
+    cudaFree(B.slot_energy); cudaFree(B.ref); cudaFree(B.cnt);
+    cudaFree(B.blocksum); cudaFree(B.blockoff); cudaFree(B.epart);
+    cudaFree(B.ctl);
+    cudaFree(h->L.energy); cudaFree(h->L.weight); cudaFree(h->L.ref_energy);
+    cudaFree(h->L.accum_energy); cudaFree(h->L.num_walkers);
+    B = DmcBufs{};
+    h->L = DmcLog{};
+    h->log_cap = 0;
+    h->dmc_ready = false;
+}
+
+int alloc_dmc(qmcb_handle *h, const qmcb_dmc_params *p,
+              long long slot_offset)
+{
+    free_dmc(h);
+    if (p->max_num_walkers < 1 || p->target_num_walkers < 1)
+        FAIL(h, QMCB_ERR_INVALID, "max/target_num_walkers must be >= 1");
+    long long cap = p->local_capacity > 0 ? p->local_capacity
+                                          : p->max_num_walkers;
+    if (cap > (1ll << 30)) FAIL(h, QMCB_ERR_INVALID, "capacity too large");
+    if (!(p->time_step > 0)) FAIL(h, QMCB_ERR_INVALID, "time_step must be > 0");
+    if (!(p->upper_bound > p->lower_bound))
+        FAIL(h, QMCB_ERR_INVALID, "upper_bound must exceed lower_bound");
+    h->dp = *p;
+    DmcBufs &B = h->B;
+    B.cap = (int) cap;
+    B.nblk = (int) ((cap + BR_TILE - 1) / BR_TILE);
+    const int N = h->M.nop;
+    size_t cb = (size_t) cap * 2 * N * sizeof(double);
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(h, cudaMalloc(&B.confs[i], cb));
+        CUDA_TRY(h, cudaMalloc(&B.energy[i], cap * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc(&B.weight[i], cap * sizeof(double)));
+        CUDA_TRY(h, cudaMemsetAsync(B.confs[i], 0, cb, h->stream));
+        CUDA_TRY(h, cudaMemsetAsync(B.energy[i], 0, cap * sizeof(double),
+                                    h->stream));
+        CUDA_TRY(h, cudaMemsetAsync(B.weight[i], 0, cap * sizeof(double),
+                                    h->stream));
+    }
+    CUDA_TRY(h, cudaMalloc(&B.slot_energy, cap * sizeof(double)));
+    CUDA_TRY(h, cudaMemsetAsync(B.slot_energy, 0, cap * sizeof(double),
+                                h->stream));
+    CUDA_TRY(h, cudaMalloc(&B.ref, cap * sizeof(int)));
+    CUDA_TRY(h, cudaMemsetAsync(B.ref, 0, cap * sizeof(int), h->stream));
+    CUDA_TRY(h, cudaMalloc(&B.cnt, cap * sizeof(int)));
+    CUDA_TRY(h, cudaMalloc(&B.blocksum, B.nblk * sizeof(long long)));
+    CUDA_TRY(h, cudaMalloc(&B.blockoff, B.nblk * sizeof(long long)));
+    CUDA_TRY(h, cudaMalloc(&B.epart, B.nblk * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&B.ctl, sizeof(DmcCtl)));
+    CUDA_TRY(h, cudaMemsetAsync(B.ctl, 0, sizeof(DmcCtl), h->stream));
+
+    DmcConsts &C = h->C;
+    C.dt = p->time_step;
+    C.sigma = std::sqrt(2 * p->time_step);   // mrbp_qmc/dmc.py:178
+    C.z_min = p->lower_bound;
+    C.size = p->upper_bound - p->lower_bound;
+    C.nwc_over_dt = p->nwc_factor / p->time_step;
+    C.target = (double) p->target_num_walkers;
+    C.seed = p->rng_seed;
+    C.slot_offset = slot_offset;
+    C.energy_mode = p->energy_mode;
+    return QMCB_OK;
+}
+
+int ensure_log(qmcb_handle *h, long long nts)
+{
+    if (nts <= h->log_cap) return QMCB_OK;
+    DmcLog &L = h->L;
+    cudaFree(L.energy); cudaFree(L.weight); cudaFree(L.ref_energy);
+    cudaFree(L.accum_energy); cudaFree(L.num_walkers);
+    L = DmcLog{};
+    h->log_cap = 0;
+    CUDA_TRY(h, cudaMalloc(&L.energy, nts * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&L.weight, nts * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&L.ref_energy, nts * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&L.accum_energy, nts * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&L.num_walkers, nts * sizeof(unsigned long long)));
+    h->log_cap = nts;
+    return QMCB_OK;
+}
+
+int read_ctl(qmcb_handle *h, DmcCtl &ctl)
+{
+    CUDA_TRY(h, cudaMemcpyAsync(&ctl, h->B.ctl, sizeof ctl,
+                                cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return QMCB_OK;
+}
+
+void fill_scalars(const qmcb_handle *h, const DmcCtl &ctl,
+                  qmcb_state_scalars *s)
+{
+    if (!s) return;
+    s->energy = ctl.last_energy;
+    s->weight = ctl.last_weight;
+    s->ref_energy = ctl.eref[ctl.step & 1];
+    s->accum_energy = ctl.last_accum;
+    s->total_energy = ctl.tot_e;
+    s->total_weight = ctl.tot_w;
+    s->num_walkers = ctl.step == 0 ? ctl.W_prev : ctl.W;
+    s->max_num_walkers = h->B.cap;
+    s->step = ctl.step;
+    s->capacity_hits = ctl.capacity_hits;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *qmcb_version(void) { return "qmcb200 0.1.0 (sm_100a)"; }
+
+const char *qmcb_last_error(const qmcb_handle *h)
+{
+    return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+int qmcb_create(const qmcb_model_params *params, int device,
+                qmcb_handle **out)
+{
+    if (!params || !out) {
+        g_create_error = "null argument";
+        return QMCB_ERR_INVALID;
+    }
+    *out = nullptr;
+    qmcb_handle *h = new qmcb_handle();
+    auto fail = [&](int code) {
+        g_create_error = h->err;
+        if (h->stream) cudaStreamDestroy(h->stream);
+        delete h;
+        return code;
+    };
+    h->device = device;
+    h->params = *params;
+    if (!build_model(*params, h->M, h->err)) return fail(QMCB_ERR_INVALID);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        h->err = std::string("no CUDA device available: ")
+                 + cudaGetErrorString(e)
+                 + " (this engine has no CPU fallback)";
+        return fail(QMCB_ERR_CUDA);
+    }
+    if (device < 0 || device >= ndev) {
+        h->err = "device index out of range";
+        return fail(QMCB_ERR_INVALID);
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        h->err = cudaGetErrorString(e);
+        return fail(QMCB_ERR_CUDA);
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        h->err = cudaGetErrorString(e);
+        return fail(QMCB_ERR_CUDA);
+    }
+    h->sm_count = prop.multiProcessorCount;
+    h->max_smem = (int) prop.sharedMemPerBlockOptin;
+    if (!choose_geom(h->M, h->max_smem, h->geom, h->err))
+        return fail(QMCB_ERR_INVALID);
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking))
+        != cudaSuccess) {
+        h->err = cudaGetErrorString(e);
+        return fail(QMCB_ERR_CUDA);
+    }
+    int rc;
+    if ((rc = set_smem(h, model_eval_kernel<true, true>)) != QMCB_OK
+        || (rc = set_smem(h, model_eval_kernel<true, false>)) != QMCB_OK
+        || (rc = set_smem(h, model_eval_kernel<false, true>)) != QMCB_OK
+        || (rc = set_smem(h, dmc_step_kernel)) != QMCB_OK)
+        return fail(rc);
+    cudaEventCreate(&h->ev0);
+    cudaEventCreate(&h->ev1);
+    *out = h;
+    return QMCB_OK;
+}
+
+void qmcb_destroy(qmcb_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_dmc(h);
+    cudaFree(h->d_scratch);
+    for (auto ev : h->step_ev) cudaEventDestroy(ev);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int qmcb_model_eval_device(qmcb_handle *h, const double *d_confs,
+                           int64_t nconf, double *d_lnpsi, double *d_energy,
+                           double *d_drift)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (nconf < 0) FAIL(h, QMCB_ERR_INVALID, "nconf < 0");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    EvalArgs a{};
+    a.confs = d_confs; a.nconf = nconf;
+    a.lnpsi = d_lnpsi; a.energy = d_energy; a.drift = d_drift;
+    bool ln = d_lnpsi != nullptr, ef = d_energy || d_drift;
+    if (!ln && !ef) return QMCB_OK;
+    return launch_model_eval(h, a, ln, ef);
+}
+
+int qmcb_model_eval(qmcb_handle *h, const double *confs, int64_t nconf,
+                    double *lnpsi, double *energy, double *drift)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (nconf < 0 || (nconf > 0 && !confs))
+        FAIL(h, QMCB_ERR_INVALID, "bad confs / nconf");
+    if (nconf == 0) return QMCB_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int N = h->M.nop;
+    size_t nc = (size_t) nconf * 2 * N, nd = (size_t) nconf * N;
+    size_t total = (nc + nd + 2 * (size_t) nconf) * sizeof(double);
+    int rc = ensure_scratch(h, total);
+    if (rc) return rc;
+    double *d_confs = h->d_scratch, *d_drift = d_confs + nc;
+    double *d_ln = d_drift + nd, *d_e = d_ln + nconf;
+    CUDA_TRY(h, cudaMemcpyAsync(d_confs, confs, nc * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+    rc = qmcb_model_eval_device(h, d_confs, nconf, lnpsi ? d_ln : nullptr,
+                                energy ? d_e : nullptr,
+                                drift ? d_drift : nullptr);
+    if (rc) return rc;
+    if (lnpsi)
+        CUDA_TRY(h, cudaMemcpyAsync(lnpsi, d_ln, nconf * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (energy)
+        CUDA_TRY(h, cudaMemcpyAsync(energy, d_e, nconf * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (drift)
+        CUDA_TRY(h, cudaMemcpyAsync(drift, d_drift, nd * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return QMCB_OK;
+}
+
+int qmcb_fourier_density(qmcb_handle *h, const double *, int64_t, int32_t,
+                         double *)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    FAIL(h, QMCB_ERR_STATE, "qmcb_fourier_density: not implemented yet");
+}
+
+int qmcb_dmc_init(qmcb_handle *h, const qmcb_dmc_params *params,
+                  const double *ini_confs, int64_t n, double ref_energy,
+                  int64_t global_slot_offset)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (!params || (n > 0 && !ini_confs) || n < 0)
+        FAIL(h, QMCB_ERR_INVALID, "bad arguments");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = alloc_dmc(h, params, global_slot_offset);
+    if (rc) return rc;
+    if (n > h->B.cap)
+        FAIL(h, QMCB_ERR_INVALID, "more initial walkers than capacity");
+    const int N = h->M.nop;
+    DmcBufs &B = h->B;
+    if (n > 0) {
+        size_t nc = (size_t) n * 2 * N * sizeof(double);
+        rc = ensure_scratch(h, nc);
+        if (rc) return rc;
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_scratch, ini_confs, nc,
+                                    cudaMemcpyHostToDevice, h->stream));
+        EvalArgs a{};
+        a.confs = h->d_scratch; a.nconf = n;
+        a.energy = B.energy[0];
+        a.state_confs = B.confs[0];
+        a.state_weight = B.weight[0];
+        a.slot_energy = B.slot_energy;
+        rc = launch_model_eval(h, a, false, true);
+        if (rc) return rc;
+    }
+    // initial scalars: mrbp_qmc/dmc.py:299-312
+    std::vector<double> e(n);
+    if (n > 0)
+        CUDA_TRY(h, cudaMemcpyAsync(e.data(), B.energy[0], n * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    double se = 0.0;
+    for (int64_t i = 0; i < n; ++i) se += e[i];
+    DmcCtl ctl{};
+    ctl.W_prev = (int) n;
+    ctl.W = (int) n;
+    ctl.last_energy = se;
+    ctl.last_weight = (double) n;
+    ctl.last_accum = n > 0 ? se / (double) n : 0.0;
+    ctl.eref[0] = std::isnan(ref_energy) ? ctl.last_accum : ref_energy;
+    ctl.eref[1] = ctl.eref[0];
+    ctl.W_global = (double) n;
+    CUDA_TRY(h, cudaMemcpyAsync(B.ctl, &ctl, sizeof ctl,
+                                cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->step_host = 0;
+    h->n_ini = (int) n;
+    h->dmc_ready = true;
+    return QMCB_OK;
+}
+
+int qmcb_dmc_set_state(qmcb_handle *h, const qmcb_dmc_params *params,
+                       const double *confs, const double *energy,
+                       const double *weight, const double *slot_energy,
+                       const qmcb_state_scalars *sc,
+                       int64_t global_slot_offset)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (!params || !sc || !confs || !energy || !weight)
+        FAIL(h, QMCB_ERR_INVALID, "bad arguments");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = alloc_dmc(h, params, global_slot_offset);
+    if (rc) return rc;
+    DmcBufs &B = h->B;
+    int64_t n = sc->num_walkers;
+    if (n < 0 || n > B.cap)
+        FAIL(h, QMCB_ERR_INVALID, "num_walkers exceeds capacity");
+    const int N = h->M.nop;
+    int par = (int) (sc->step & 1);
+    CUDA_TRY(h, cudaMemcpyAsync(B.confs[par], confs,
+                                (size_t) n * 2 * N * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(B.energy[par], energy, n * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(B.weight[par], weight, n * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+    if (slot_energy)
+        CUDA_TRY(h, cudaMemcpyAsync(B.slot_energy, slot_energy,
+                                    B.cap * sizeof(double),
+                                    cudaMemcpyHostToDevice, h->stream));
+    else
+        CUDA_TRY(h, cudaMemcpyAsync(B.slot_energy, energy, n * sizeof(double),
+                                    cudaMemcpyHostToDevice, h->stream));
+    DmcCtl ctl{};
+    ctl.step = sc->step;
+    ctl.capacity_hits = sc->capacity_hits;
+    ctl.W_prev = (int) n;
+    ctl.W = (int) n;
+    ctl.eref[0] = ctl.eref[1] = sc->ref_energy;
+    ctl.tot_e = sc->total_energy;
+    ctl.tot_w = sc->total_weight;
+    ctl.last_energy = sc->energy;
+    ctl.last_weight = sc->weight;
+    ctl.last_accum = sc->accum_energy;
+    ctl.W_global = sc->weight;
+    CUDA_TRY(h, cudaMemcpyAsync(B.ctl, &ctl, sizeof ctl,
+                                cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->step_host = sc->step;
+    h->n_ini = (int) n;
+    h->dmc_ready = true;
+    return QMCB_OK;
+}
+
+int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
+                       double *energy, double *weight, uint64_t *num_walkers,
+                       double *ref_energy, double *accum_energy,
+                       double *density, double *ssf)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (!h->dmc_ready) FAIL(h, QMCB_ERR_STATE, "qmcb_dmc_init not called");
+    if (nts < 1) FAIL(h, QMCB_ERR_INVALID, "nts must be >= 1");
+    (void) eval_estimators; (void) density; (void) ssf;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_log(h, nts);
+    if (rc) return rc;
+    DmcBufs &B = h->B;
+    DmcLog L = h->L;
+    L.block_step0 = h->step_host;
+    const GroupGeom &g = h->geom;
+    const int step_grid = (B.cap + g.G - 1) / g.G;
+    if (h->profile_steps) {
+        while ((long long) h->step_ev.size() < 2 * nts) {
+            cudaEvent_t ev;
+            CUDA_TRY(h, cudaEventCreate(&ev));
+            h->step_ev.push_back(ev);
+        }
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    for (int64_t i = 0; i < nts; ++i) {
+        branch_count_kernel<<<B.nblk, BR_THREADS, 0, h->stream>>>(B, h->C);
+        branch_scan_kernel<<<1, BR_THREADS, 0, h->stream>>>(B);
+        branch_fill_kernel<<<B.nblk, BR_THREADS, 0, h->stream>>>(B);
+        dmc_local_sum_kernel<<<1, BR_THREADS, 0, h->stream>>>(B);
+        if (h->profile_steps)
+            CUDA_TRY(h, cudaEventRecord(h->step_ev[2 * i], h->stream));
+        dmc_step_kernel<<<step_grid, g.nthreads, g.smem_bytes, h->stream>>>(
+            h->M, g, B, h->C);
+        if (h->profile_steps)
+            CUDA_TRY(h, cudaEventRecord(h->step_ev[2 * i + 1], h->stream));
+        dmc_finalize_kernel<<<1, 32, 0, h->stream>>>(B, h->C, L);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    h->step_host += nts;
+    h->last_launches = 6 * nts;
+    if (energy)
+        CUDA_TRY(h, cudaMemcpyAsync(energy, L.energy, nts * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (weight)
+        CUDA_TRY(h, cudaMemcpyAsync(weight, L.weight, nts * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (num_walkers)
+        CUDA_TRY(h, cudaMemcpyAsync(num_walkers, L.num_walkers,
+                                    nts * sizeof(uint64_t),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (ref_energy)
+        CUDA_TRY(h, cudaMemcpyAsync(ref_energy, L.ref_energy,
+                                    nts * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (accum_energy)
+        CUDA_TRY(h, cudaMemcpyAsync(accum_energy, L.accum_energy,
+                                    nts * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_total_ms = ms;
+    h->last_step_ms = 0.0;
+    if (h->profile_steps) {
+        double acc = 0.0;
+        for (int64_t i = 0; i < nts; ++i) {
+            float sms = 0.f;
+            CUDA_TRY(h, cudaEventElapsedTime(&sms, h->step_ev[2 * i],
+                                             h->step_ev[2 * i + 1]));
+            acc += sms;
+        }
+        h->last_step_ms = acc;
+    }
+    return QMCB_OK;
+}
+
+int qmcb_set_profiling(qmcb_handle *h, int32_t on)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    h->profile_steps = on != 0;
+    return QMCB_OK;
+}
+
+int qmcb_last_block_stats(qmcb_handle *h, double *total_ms,
+                          double *step_kernel_ms, int64_t *launches)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (total_ms) *total_ms = h->last_total_ms;
+    if (step_kernel_ms) *step_kernel_ms = h->last_step_ms;
+    if (launches) *launches = h->last_launches;
+    return QMCB_OK;
+}
+
+int qmcb_dmc_get_state(qmcb_handle *h, double *confs, double *energy,
+                       double *weight, uint8_t *mask, int64_t *cloning_ref,
+                       qmcb_state_scalars *scalars)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (!h->dmc_ready) FAIL(h, QMCB_ERR_STATE, "qmcb_dmc_init not called");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    DmcCtl ctl;
+    int rc = read_ctl(h, ctl);
+    if (rc) return rc;
+    fill_scalars(h, ctl, scalars);
+    DmcBufs &B = h->B;
+    const int N = h->M.nop;
+    const long long cap = B.cap;
+    bool identity = ctl.step == 0;
+    // the last executed step `step-1` branched from buffer (step-1)&1
+    int par = identity ? 0 : (int) ((ctl.step - 1) & 1);
+    int W = identity ? ctl.W_prev : ctl.W;
+    size_t nc = (size_t) cap * 2 * N * sizeof(double);
+    size_t total = nc + 2 * cap * sizeof(double) + cap * sizeof(long long)
+                   + cap;
+    rc = ensure_scratch(h, total);
+    if (rc) return rc;
+    double *d_c = h->d_scratch;
+    double *d_e = d_c + (size_t) cap * 2 * N;
+    double *d_w = d_e + cap;
+    long long *d_r = reinterpret_cast<long long *>(d_w + cap);
+    unsigned char *d_m = reinterpret_cast<unsigned char *>(d_r + cap);
+    gather_state_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(
+        B.confs[par], B.energy[par], B.ref, W, B.cap, N, identity,
+        confs ? d_c : nullptr, d_e, d_w, d_m, d_r);
+    CUDA_TRY(h, cudaGetLastError());
+    if (confs)
+        CUDA_TRY(h, cudaMemcpyAsync(confs, d_c, nc, cudaMemcpyDeviceToHost,
+                                    h->stream));
+    if (energy)
+        CUDA_TRY(h, cudaMemcpyAsync(energy, d_e, cap * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (weight)
+        CUDA_TRY(h, cudaMemcpyAsync(weight, d_w, cap * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (mask)
+        CUDA_TRY(h, cudaMemcpyAsync(mask, d_m, cap, cudaMemcpyDeviceToHost,
+                                    h->stream));
+    if (cloning_ref)
+        CUDA_TRY(h, cudaMemcpyAsync(cloning_ref, d_r, cap * sizeof(long long),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return QMCB_OK;
+}
+
+int qmcb_dmc_get_next(qmcb_handle *h, double *confs, double *energy,
+                      double *weight, double *slot_energy,
+                      qmcb_state_scalars *scalars)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (!h->dmc_ready) FAIL(h, QMCB_ERR_STATE, "qmcb_dmc_init not called");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    DmcCtl ctl;
+    int rc = read_ctl(h, ctl);
+    if (rc) return rc;
+    fill_scalars(h, ctl, scalars);
+    if (scalars) scalars->num_walkers = ctl.W_prev;
+    DmcBufs &B = h->B;
+    const int N = h->M.nop;
+    int par = (int) (ctl.step & 1);
+    size_t n = (size_t) ctl.W_prev;
+    if (confs)
+        CUDA_TRY(h, cudaMemcpyAsync(confs, B.confs[par],
+                                    n * 2 * N * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (energy)
+        CUDA_TRY(h, cudaMemcpyAsync(energy, B.energy[par], n * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (weight)
+        CUDA_TRY(h, cudaMemcpyAsync(weight, B.weight[par], n * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (slot_energy)
+        CUDA_TRY(h, cudaMemcpyAsync(slot_energy, B.slot_energy,
+                                    B.cap * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return QMCB_OK;
+}
+
+int qmcb_measure_fp64_peak(int device, double *tflops, double *ms_out)
+{
+    if (!tflops) return QMCB_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return QMCB_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return QMCB_ERR_CUDA;
+    const int grid = prop.multiProcessorCount * 8, iters = 4096;
+    double *d = nullptr;
+    if (cudaMalloc(&d, (size_t) grid * 256 * sizeof(double)) != cudaSuccess)
+        return QMCB_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<grid, 256>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) {
+            cudaFree(d);
+            return QMCB_ERR_CUDA;
+        }
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep >= 2 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    double flops = 2.0 * 64.0 * iters * (double) grid * 256.0;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return QMCB_OK;
+}
+
+int qmcb_comm_unique_id(uint8_t *) { return QMCB_ERR_NCCL; }
+
+int qmcb_comm_init(qmcb_handle *h, const uint8_t *, int32_t, int32_t)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    FAIL(h, QMCB_ERR_NCCL, "qmcb_comm_init: not implemented yet");
+}
+
+int qmcb_dmc_rebalance(qmcb_handle *h, int64_t *)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    FAIL(h, QMCB_ERR_NCCL, "qmcb_dmc_rebalance: not implemented yet");
+}
+
+int qmcb_vmc_init(qmcb_handle *h, const qmcb_vmc_params *, const double *,
+                  int64_t)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    FAIL(h, QMCB_ERR_STATE, "qmcb_vmc_init: not implemented yet");
+}
+
+int qmcb_vmc_run_block(qmcb_handle *h, int64_t, double *, double *, uint8_t *,
+                       double *, double *, double *, double *)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    FAIL(h, QMCB_ERR_STATE, "qmcb_vmc_run_block: not implemented yet");
+}
+
+int qmcb_vmc_get_state(qmcb_handle *h, double *, double *)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    FAIL(h, QMCB_ERR_STATE, "qmcb_vmc_get_state: not implemented yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,467 @@
+// Kernels of the B200 walker-ensemble engine (model evaluation, DMC step,
+// branching, population control).  See qmcb_dev.cuh for the math.
+#pragma once
+#include "qmcb_dev.cuh"
+
+namespace qmcb {
+
+// Thread (g, I) of a walker-group CTA.
+struct GroupIdx {
+    int g, I;
+    bool in_group;      // thread maps to a (walker, block) pair at all
+};
+
+__device__ __forceinline__ GroupIdx group_index(const DevModel &M, int G)
+{
+    GroupIdx x;
+    int t = threadIdx.x;
+    x.g = t / M.nb;
+    x.I = t - x.g * M.nb;
+    x.in_group = x.g < G;
+    if (!x.in_group) { x.g = 0; x.I = 0; }
+    return x;
+}
+
+__device__ __forceinline__ GroupSmem group_smem(const DevModel &M, int nbp)
+{
+    extern __shared__ double qmcb_smem[];
+    GroupSmem sm;
+    sm.base = qmcb_smem;
+    sm.nbp = nbp;
+    sm.kslots = M.kmax + 1;
+    return sm;
+}
+
+// Load / store the thread's 4 values of one row of a (2, N) configuration.
+__device__ __forceinline__ void load4(const double *row, int I, int nvalid,
+                                      bool vec_ok, double (&x)[TB])
+{
+    if (vec_ok && nvalid == TB) {
+        const double2 *p = reinterpret_cast<const double2 *>(row + TB * I);
+        double2 a = p[0], b = p[1];
+        x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+    } else {
+#pragma unroll
+        for (int c = 0; c < TB; ++c)
+            x[c] = (c < nvalid) ? row[TB * I + c] : 0.0;
+    }
+}
+
+__device__ __forceinline__ void store4(double *row, int I, int nvalid,
+                                       bool vec_ok, const double (&x)[TB])
+{
+    if (vec_ok && nvalid == TB) {
+        double2 *p = reinterpret_cast<double2 *>(row + TB * I);
+        p[0] = make_double2(x[0], x[1]);
+        p[1] = make_double2(x[2], x[3]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < TB; ++c)
+            if (c < nvalid) row[TB * I + c] = x[c];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K1 / K9: lnPsi, E_L, drift of a batch of configurations.
+// Output layout selectable: separate arrays (model_eval) or a DMC state
+// buffer (init: confs[s] = (z, F), energy[s], weight[s] = 1).
+// ---------------------------------------------------------------------------
+struct EvalArgs {
+    const double *confs;    // [nconf][2][N]
+    long long nconf;
+    double *lnpsi;          // [nconf] or null
+    double *energy;         // [nconf] or null
+    double *drift;          // [nconf][N] or null
+    double *state_confs;    // [cap][2][N] or null: write (z, F)
+    double *state_weight;   // [cap] or null: write 1
+    double *slot_energy;    // [cap] or null: write E
+};
+
+template <bool LN, bool EF>
+__global__ void __launch_bounds__(256)
+model_eval_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
+                  EvalArgs a)
+{
+    GroupSmem sm = group_smem(M, geom.nbp);
+    GroupIdx x = group_index(M, geom.G);
+    const int N = M.nop;
+    const bool vec_ok = (N % 2) == 0;
+    for (long long base = (long long) blockIdx.x * geom.G; base < a.nconf;
+         base += (long long) gridDim.x * geom.G) {
+        long long b = base + x.g;
+        bool active = x.in_group && b < a.nconf;
+        int nvalid = min(TB, N - TB * x.I);
+        double z[TB] = {0., 0., 0., 0.};
+        if (active) load4(a.confs + b * 2 * N, x.I, nvalid, vec_ok, z);
+        EvalOut o;
+        group_eval<LN, EF>(M, sm, x.g, x.I, active, z, nvalid, o);
+        if (active) {
+            if (EF && a.drift)
+                store4(a.drift + b * N, x.I, nvalid, vec_ok, o.F);
+            if (a.state_confs) {
+                store4(a.state_confs + b * 2 * N, x.I, nvalid, vec_ok, z);
+                store4(a.state_confs + b * 2 * N + N, x.I, nvalid, vec_ok,
+                       o.F);
+            }
+            if (x.I == 0) {
+                if (LN && a.lnpsi) a.lnpsi[b] = o.lnpsi;
+                if (EF && a.energy) a.energy[b] = o.energy;
+                if (EF && a.slot_energy) a.slot_energy[b] = o.energy;
+                if (a.state_weight) a.state_weight[b] = 1.0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// DMC control block (device memory).  Everything a time step needs lives
+// here, so a step is a fixed sequence of launches with constant arguments.
+// ---------------------------------------------------------------------------
+struct DmcCtl {
+    long long step;             // time steps completed since init
+    long long capacity_hits;
+    long long total_children;   // before truncation at capacity
+    int W_prev;                 // live walkers of the population to branch
+    int W;                      // live walkers after branching (this step)
+    double eref[2];             // eref[step & 1] drives step `step`
+    double tot_e, tot_w;        // running totals (qmc_base/dmc.py:733-765)
+    double red[2];              // {sum E_parents, W}: local, then global
+    double last_energy, last_weight, last_accum;
+    double W_global;            // global live walkers of the last step
+};
+
+struct DmcBufs {
+    double *confs[2];           // [cap][2][N]
+    double *energy[2];          // [cap]
+    double *weight[2];          // [cap]
+    double *slot_energy;        // [cap]  persistent per-slot array (quirk Q1)
+    int *ref;                   // [cap]  child slot -> parent slot
+    int *cnt;                   // [cap]  clone counts
+    long long *blocksum;        // [nblk]
+    long long *blockoff;        // [nblk]
+    double *epart;              // [nblk]
+    DmcCtl *ctl;
+    int cap;
+    int nblk;
+};
+
+struct DmcConsts {
+    double dt, sigma, z_min, size, nwc_over_dt, target;
+    uint64_t seed;
+    long long slot_offset;      // global index of local slot 0
+    int energy_mode;
+};
+
+struct DmcLog {
+    double *energy, *weight, *ref_energy, *accum_energy;
+    unsigned long long *num_walkers;
+    long long block_step0;      // ctl.step at block start
+};
+
+constexpr int BR_THREADS = 256;
+constexpr int BR_ITEMS = 4;
+constexpr int BR_TILE = BR_THREADS * BR_ITEMS;
+
+__device__ __forceinline__ long long block_excl_scan(long long v,
+                                                     long long *total)
+{
+    // exclusive scan of one value per thread over a BR_THREADS CTA
+    __shared__ long long wsum[BR_THREADS / 32];
+    __shared__ long long tot;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        long long n = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += n;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        long long w = (lane < BR_THREADS / 32) ? wsum[lane] : 0;
+        long long winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            long long n = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += n;
+        }
+        if (lane < BR_THREADS / 32) wsum[lane] = winc - w;
+        if (lane == 31) tot = winc;
+    }
+    __syncthreads();
+    long long r = inc - v + wsum[wid];
+    if (total) *total = tot;
+    __syncthreads();
+    return r;
+}
+
+// K4a: clone counts c_s = int(w_s + u_s) (qmc_base/dmc.py:641-643).
+__global__ void __launch_bounds__(BR_THREADS)
+branch_count_kernel(DmcBufs B, DmcConsts C)
+{
+    const DmcCtl *ctl = B.ctl;
+    const int Wp = ctl->W_prev;
+    const int par = (int) (ctl->step & 1);
+    const uint32_t step = (uint32_t) ctl->step;
+    const double *w = B.weight[par];
+    long long local = 0;
+    int base = blockIdx.x * BR_TILE + threadIdx.x * BR_ITEMS;
+#pragma unroll
+    for (int i = 0; i < BR_ITEMS; ++i) {
+        int s = base + i;
+        int c = 0;
+        if (s < Wp) {
+            double u0, u1;
+            rng_uniform2(C.seed, (uint32_t) (C.slot_offset + s), 0u, step,
+                         STREAM_BRANCH, u0, u1);
+            double x = w[s] + u0;
+            c = (x >= (double) B.cap) ? B.cap : (int) x;
+            if (c < 0) c = 0;
+        }
+        if (s < B.cap) B.cnt[s] = c;
+        local += c;
+    }
+    long long tot;
+    block_excl_scan(local, &tot);
+    if (threadIdx.x == 0) B.blocksum[blockIdx.x] = tot;
+}
+
+// K4b: scan of the per-CTA sums; fixes W for this step.
+__global__ void __launch_bounds__(BR_THREADS)
+branch_scan_kernel(DmcBufs B)
+{
+    __shared__ long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < B.nblk; b0 += BR_THREADS) {
+        int b = b0 + threadIdx.x;
+        long long v = (b < B.nblk) ? B.blocksum[b] : 0;
+        long long tot;
+        long long ex = block_excl_scan(v, &tot);
+        long long carry = carry_s;
+        if (b < B.nblk) B.blockoff[b] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        DmcCtl *ctl = B.ctl;
+        long long total = carry_s;
+        ctl->total_children = total;
+        if (total > B.cap) { ctl->capacity_hits += 1; total = B.cap; }
+        ctl->W = (int) total;
+    }
+}
+
+// K4c: children occupy consecutive slots in parent order, truncated at the
+// capacity (qmc_base/dmc.py:644-653); per-CTA partial of sum E over the
+// cloned parents (= state_energy, qmc_base/dmc.py:759-760).
+__global__ void __launch_bounds__(BR_THREADS)
+branch_fill_kernel(DmcBufs B)
+{
+    const DmcCtl *ctl = B.ctl;
+    const int par = (int) (ctl->step & 1);
+    const double *e = B.energy[par];
+    int base = blockIdx.x * BR_TILE + threadIdx.x * BR_ITEMS;
+    int c[BR_ITEMS];
+    long long local = 0;
+#pragma unroll
+    for (int i = 0; i < BR_ITEMS; ++i) {
+        int s = base + i;
+        c[i] = (s < B.cap) ? B.cnt[s] : 0;
+        local += c[i];
+    }
+    long long off = block_excl_scan(local, nullptr) + B.blockoff[blockIdx.x];
+    double esum = 0.0;
+#pragma unroll
+    for (int i = 0; i < BR_ITEMS; ++i) {
+        int s = base + i;
+        int placed = 0;
+        for (int k = 0; k < c[i]; ++k) {
+            long long slot = off + k;
+            if (slot >= B.cap) break;
+            B.ref[slot] = s;
+            ++placed;
+        }
+        if (placed) esum += (double) placed * e[s];
+        off += c[i];
+    }
+    // fixed-shape CTA reduction: deterministic
+    __shared__ double red[BR_THREADS];
+    red[threadIdx.x] = esum;
+    __syncthreads();
+    for (int d = BR_THREADS / 2; d > 0; d >>= 1) {
+        if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) B.epart[blockIdx.x] = red[0];
+}
+
+// K7a: local {sum E_parents, W} into ctl->red (fixed order).
+__global__ void __launch_bounds__(BR_THREADS)
+dmc_local_sum_kernel(DmcBufs B)
+{
+    __shared__ double red[BR_THREADS];
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < B.nblk; b += BR_THREADS) acc += B.epart[b];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = BR_THREADS / 2; d > 0; d >>= 1) {
+        if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        B.ctl->red[0] = red[0];
+        B.ctl->red[1] = (double) B.ctl->W;
+    }
+}
+
+// K7b: population control (qmc_base/dmc.py:758-771) from the (global) sums in
+// ctl->red, the per-step log, and the hand-over to the next step.
+__global__ void dmc_finalize_kernel(DmcBufs B, DmcConsts C, DmcLog L)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    DmcCtl *ctl = B.ctl;
+    double sE = ctl->red[0], sW = ctl->red[1];
+    ctl->tot_e += sE;
+    ctl->tot_w += sW;
+    double accum = ctl->tot_e / ctl->tot_w;
+    double eref = accum - C.nwc_over_dt * log(sW / C.target);
+    long long t = ctl->step;
+    ctl->eref[(t + 1) & 1] = eref;
+    ctl->last_energy = sE;
+    ctl->last_weight = sW;
+    ctl->last_accum = accum;
+    ctl->W_global = sW;
+    long long i = t - L.block_step0;
+    if (L.energy) {
+        L.energy[i] = sE;
+        L.weight[i] = sW;
+        L.num_walkers[i] = (unsigned long long) (sW + 0.5);
+        L.ref_energy[i] = eref;
+        L.accum_energy[i] = accum;
+    }
+    ctl->W_prev = ctl->W;
+    ctl->step = t + 1;
+}
+
+// ---------------------------------------------------------------------------
+// K3: the fused DMC step.  For every live child slot s with parent r:
+//   gather (z, F) of r -> drift-diffusion move + recast -> tables ->
+//   pair drift / local energy -> branching weight -> write the child.
+// Reference: evolve_state_inner / evolve_system / ith_diffusion
+// (qmc_base/jastrow/dmc.py:634-673, 743-951), recast (mrbp_qmc/dmc.py:453).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dmc_step_kernel(const __grid_constant__ DevModel M, GroupGeom geom, DmcBufs B,
+                DmcConsts C)
+{
+    const DmcCtl *ctl = B.ctl;
+    const int W = ctl->W;
+    const long long s0 = (long long) blockIdx.x * geom.G;
+    if (s0 >= W) return;
+    const long long t = ctl->step;
+    const int par = (int) (t & 1);
+    const double eref = ctl->eref[par];
+    const double *pconfs = B.confs[par];
+    const double *penergy = B.energy[par];
+    double *nconfs = B.confs[par ^ 1];
+    double *nenergy = B.energy[par ^ 1];
+    double *nweight = B.weight[par ^ 1];
+
+    GroupSmem sm = group_smem(M, geom.nbp);
+    GroupIdx x = group_index(M, geom.G);
+    const int N = M.nop;
+    const bool vec_ok = (N % 2) == 0;
+    const long long s = s0 + x.g;
+    const bool active = x.in_group && s < W;
+    const int nvalid = min(TB, N - TB * x.I);
+
+    double z[TB] = {0., 0., 0., 0.};
+    int r = 0;
+    if (active) {
+        r = B.ref[s];
+        double zp[TB], fp[TB];
+        const double *pc = pconfs + (long long) r * 2 * N;
+        load4(pc, x.I, nvalid, vec_ok, zp);
+        load4(pc + N, x.I, nvalid, vec_ok, fp);
+        double nrm[TB];
+        const uint32_t gs = (uint32_t) (C.slot_offset + s);
+        rng_normal2(C.seed, gs, (uint32_t) (2 * x.I), (uint32_t) t,
+                    STREAM_DIFFUSE, nrm[0], nrm[1]);
+        rng_normal2(C.seed, gs, (uint32_t) (2 * x.I + 1), (uint32_t) t,
+                    STREAM_DIFFUSE, nrm[2], nrm[3]);
+#pragma unroll
+        for (int c = 0; c < TB; ++c) {
+            double zn = zp[c] + 2.0 * fp[c] * C.dt + C.sigma * nrm[c];
+            z[c] = recast(zn, C.z_min, C.size);
+        }
+    }
+    EvalOut o;
+    group_eval<false, true>(M, sm, x.g, x.I, active, z, nvalid, o);
+    if (active) {
+        double *nc = nconfs + s * 2 * N;
+        store4(nc, x.I, nvalid, vec_ok, z);
+        store4(nc + N, x.I, nvalid, vec_ok, o.F);
+        if (x.I == 0) {
+            double e_parent = penergy[r];
+            double e_old = (C.energy_mode == 0) ? B.slot_energy[s] : e_parent;
+            double mean = (o.energy + e_old) / 2;
+            nenergy[s] = o.energy;
+            nweight[s] = exp(-C.dt * (mean - eref));
+            B.slot_energy[s] = e_parent;
+        }
+    }
+}
+
+// Gather of the yielded ("actual") population: slot s <- parent ref[s].
+__global__ void gather_state_kernel(const double *pconfs,
+                                    const double *penergy, const int *ref,
+                                    int W, int cap, int N, bool identity,
+                                    double *oconfs, double *oenergy,
+                                    double *oweight, unsigned char *omask,
+                                    long long *oref)
+{
+    long long total = (long long) cap * 2 * N;
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+         i < total; i += (long long) gridDim.x * blockDim.x) {
+        long long s = i / (2 * N);
+        int k = (int) (i - s * 2 * N);
+        double v = 0.0;
+        if (s < W) {
+            int r = identity ? (int) s : ref[s];
+            v = pconfs[(long long) r * 2 * N + k];
+        }
+        if (oconfs) oconfs[i] = v;
+        if (k == 0) {
+            int r = (s < W) ? (identity ? (int) s : ref[s]) : 0;
+            if (oenergy) oenergy[s] = (s < W) ? penergy[r] : 0.0;
+            if (oweight) oweight[s] = (s < W) ? 1.0 : 0.0;
+            if (omask) omask[s] = (s < W) ? 0 : 1;
+            if (oref) oref[s] = (s < W) ? r : 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Roofline denominator: sustained DFMA rate (8 independent chains/thread).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
+    double x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b);
+            x3 = fma(x3, a, b); x4 = fma(x4, a, b); x5 = fma(x5, a, b);
+            x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace qmcb

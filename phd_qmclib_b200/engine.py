@@ -1,0 +1,266 @@
+"""Thin object wrapper over the C ABI: one :class:`Engine` = one
+``qmcb_handle`` = one model on one GPU.  numpy in, numpy out; no compute on
+the Python side."""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import DMCParams, EngineError, StateScalars, VMCParams, ptr
+from .model import param_block
+
+__all__ = ['Engine', 'EngineError']
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Engine:
+    """The CUDA engine for one model spec on one device."""
+
+    def __init__(self, spec, device: int = 0):
+        self._L = _lib.load()
+        self.block = param_block(spec)
+        self.nop = int(self.block[3])
+        self.supercell_size = float(self.block[4])
+        self.device = int(device)
+        mp = _lib.model_params_struct(self.block)
+        h = C.c_void_p()
+        rc = self._L.qmcb_create(C.byref(mp), self.device, C.byref(h))
+        if rc != 0:
+            msg = self._L.qmcb_last_error(None).decode()
+            raise EngineError(f'qmcb_create failed ({rc}): {msg}')
+        self._h = h
+        self._dmc_cap = None
+
+    # -- plumbing ---------------------------------------------------------
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.qmcb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._L.qmcb_last_error(self._h).decode()
+            raise EngineError(f'{what} failed ({rc}): {msg}')
+
+    @property
+    def handle(self):
+        return self._h
+
+    # -- fixed-configuration evaluation ------------------------------------
+    def model_eval(self, confs, want=('lnpsi', 'energy', 'drift')):
+        """``confs`` (B, 2, N) or (2, N) -> dict of lnpsi (B,), energy (B,),
+        drift (B, N).  Reference: ``core_funcs.wf_abs_log / energy / drift``.
+        """
+        confs = _f64(confs)
+        if confs.ndim == 2:
+            confs = confs[None]
+        if confs.ndim != 3 or confs.shape[1:] != (2, self.nop):
+            raise ValueError(f'confs must have shape (B, 2, {self.nop})')
+        n = confs.shape[0]
+        out = dict(
+            lnpsi=np.empty(n) if 'lnpsi' in want else None,
+            energy=np.empty(n) if 'energy' in want else None,
+            drift=np.empty((n, self.nop)) if 'drift' in want else None)
+        rc = self._L.qmcb_model_eval(self._h, ptr(confs), n,
+                                     ptr(out['lnpsi']), ptr(out['energy']),
+                                     ptr(out['drift']))
+        self._check(rc, 'qmcb_model_eval')
+        return out
+
+    def model_eval_device(self, d_confs, nconf, d_lnpsi=0, d_energy=0,
+                          d_drift=0):
+        """Device-pointer variant (integers, e.g. ``tensor.data_ptr()``)."""
+        rc = self._L.qmcb_model_eval_device(
+            self._h, C.c_void_p(d_confs), nconf, C.c_void_p(d_lnpsi or None),
+            C.c_void_p(d_energy or None), C.c_void_p(d_drift or None))
+        self._check(rc, 'qmcb_model_eval_device')
+
+    def fourier_density(self, confs, num_modes):
+        confs = _f64(confs)
+        if confs.ndim == 2:
+            confs = confs[None]
+        out = np.empty((confs.shape[0], num_modes, 3))
+        rc = self._L.qmcb_fourier_density(self._h, ptr(confs),
+                                          confs.shape[0], num_modes, ptr(out))
+        self._check(rc, 'qmcb_fourier_density')
+        return out
+
+    # -- DMC ----------------------------------------------------------------
+    @staticmethod
+    def dmc_params(time_step, max_num_walkers, target_num_walkers,
+                   nwc_factor, rng_seed, lower_bound, upper_bound,
+                   energy_mode=0, ssf=None, density=None, local_capacity=0):
+        """``ssf`` / ``density``: ``(num, as_pure, pfw_nts)`` or None."""
+        p = DMCParams()
+        p.time_step = time_step
+        p.nwc_factor = nwc_factor
+        p.lower_bound, p.upper_bound = lower_bound, upper_bound
+        p.max_num_walkers = max_num_walkers
+        p.target_num_walkers = target_num_walkers
+        p.rng_seed = int(rng_seed) & 0xFFFFFFFFFFFFFFFF
+        p.energy_mode = energy_mode
+        if ssf:
+            p.ssf_num_modes, p.ssf_as_pure, p.ssf_pfw_nts = (
+                int(ssf[0]), int(bool(ssf[1])), int(ssf[2]))
+        if density:
+            p.density_num_bins, p.density_as_pure, p.density_pfw_nts = (
+                int(density[0]), int(bool(density[1])), int(density[2]))
+        p.local_capacity = local_capacity
+        return p
+
+    def dmc_init(self, params: DMCParams, ini_confs, ref_energy=None,
+                 global_slot_offset=0):
+        ini_confs = _f64(ini_confs)
+        if ini_confs.ndim != 3 or ini_confs.shape[1:] != (2, self.nop):
+            raise ValueError(f'ini_confs must have shape (n, 2, {self.nop})')
+        ref = math.nan if ref_energy is None else float(ref_energy)
+        rc = self._L.qmcb_dmc_init(self._h, C.byref(params), ptr(ini_confs),
+                                   ini_confs.shape[0], ref,
+                                   global_slot_offset)
+        self._check(rc, 'qmcb_dmc_init')
+        self._dmc_params = params
+        self._dmc_cap = int(params.local_capacity or params.max_num_walkers)
+
+    def dmc_set_state(self, params: DMCParams, confs, energy, weight,
+                      scalars: StateScalars, slot_energy=None,
+                      global_slot_offset=0):
+        confs, energy, weight = _f64(confs), _f64(energy), _f64(weight)
+        if slot_energy is not None:
+            slot_energy = _f64(slot_energy)
+        rc = self._L.qmcb_dmc_set_state(
+            self._h, C.byref(params), ptr(confs), ptr(energy), ptr(weight),
+            ptr(slot_energy), C.byref(scalars), global_slot_offset)
+        self._check(rc, 'qmcb_dmc_set_state')
+        self._dmc_params = params
+        self._dmc_cap = int(params.local_capacity or params.max_num_walkers)
+
+    def dmc_run_block(self, nts, eval_estimators=False, out=None,
+                      density=None, ssf=None):
+        """Advance ``nts`` time steps; returns the per-step series (dict of
+        arrays of length nts).  ``out`` may hold preallocated arrays."""
+        if out is None:
+            out = dict(energy=np.zeros(nts), weight=np.zeros(nts),
+                       num_walkers=np.zeros(nts, dtype=np.uint64),
+                       ref_energy=np.zeros(nts), accum_energy=np.zeros(nts))
+        rc = self._L.qmcb_dmc_run_block(
+            self._h, nts, int(bool(eval_estimators)), ptr(out['energy']),
+            ptr(out['weight']), ptr(out['num_walkers']),
+            ptr(out['ref_energy']), ptr(out['accum_energy']), ptr(density),
+            ptr(ssf))
+        self._check(rc, 'qmcb_dmc_run_block')
+        return out
+
+    def dmc_advance(self, nts):
+        """Advance without copying any series back (benchmark helper)."""
+        rc = self._L.qmcb_dmc_run_block(self._h, nts, 0, None, None, None,
+                                        None, None, None, None)
+        self._check(rc, 'qmcb_dmc_run_block')
+
+    def dmc_get_state(self, want_confs=True):
+        cap, n = self._dmc_cap, self.nop
+        out = dict(confs=np.empty((cap, 2, n)) if want_confs else None,
+                   energy=np.empty(cap), weight=np.empty(cap),
+                   mask=np.empty(cap, dtype=np.uint8),
+                   cloning_ref=np.empty(cap, dtype=np.int64))
+        sc = StateScalars()
+        rc = self._L.qmcb_dmc_get_state(
+            self._h, ptr(out['confs']), ptr(out['energy']),
+            ptr(out['weight']), ptr(out['mask']), ptr(out['cloning_ref']),
+            C.byref(sc))
+        self._check(rc, 'qmcb_dmc_get_state')
+        out['scalars'] = sc
+        return out
+
+    def dmc_scalars(self):
+        sc = StateScalars()
+        rc = self._L.qmcb_dmc_get_state(self._h, None, None, None, None,
+                                        None, C.byref(sc))
+        self._check(rc, 'qmcb_dmc_get_state')
+        return sc
+
+    def dmc_get_next(self):
+        sc = StateScalars()
+        rc = self._L.qmcb_dmc_get_next(self._h, None, None, None, None,
+                                       C.byref(sc))
+        self._check(rc, 'qmcb_dmc_get_next')
+        n, cap = int(sc.num_walkers), self._dmc_cap
+        out = dict(confs=np.empty((n, 2, self.nop)), energy=np.empty(n),
+                   weight=np.empty(n), slot_energy=np.empty(cap))
+        rc = self._L.qmcb_dmc_get_next(
+            self._h, ptr(out['confs']), ptr(out['energy']),
+            ptr(out['weight']), ptr(out['slot_energy']), C.byref(sc))
+        self._check(rc, 'qmcb_dmc_get_next')
+        out['scalars'] = sc
+        return out
+
+    def set_profiling(self, on=True):
+        self._check(self._L.qmcb_set_profiling(self._h, int(on)),
+                    'qmcb_set_profiling')
+
+    def last_block_stats(self):
+        t, s, n = C.c_double(), C.c_double(), C.c_int64()
+        rc = self._L.qmcb_last_block_stats(self._h, C.byref(t), C.byref(s),
+                                           C.byref(n))
+        self._check(rc, 'qmcb_last_block_stats')
+        return dict(total_ms=t.value, step_kernel_ms=s.value,
+                    launches=n.value)
+
+    # -- VMC ----------------------------------------------------------------
+    def vmc_init(self, confs, move_spread, rng_seed, lower_bound,
+                 upper_bound, ssf_num_modes=0, chain_offset=0):
+        confs = _f64(confs)
+        if confs.ndim == 2:
+            confs = confs[None]
+        p = VMCParams()
+        p.move_spread = move_spread
+        p.lower_bound, p.upper_bound = lower_bound, upper_bound
+        p.rng_seed = int(rng_seed) & 0xFFFFFFFFFFFFFFFF
+        p.chain_offset = chain_offset
+        p.ssf_num_modes = ssf_num_modes
+        rc = self._L.qmcb_vmc_init(self._h, C.byref(p), ptr(confs),
+                                   confs.shape[0])
+        self._check(rc, 'qmcb_vmc_init')
+        self._vmc_chains = confs.shape[0]
+        self._vmc_modes = ssf_num_modes
+
+    def vmc_run_block(self, ns, series=True, sums=False):
+        c, m = self._vmc_chains, self._vmc_modes
+        out = {}
+        if series:
+            out.update(lnpsi=np.empty((c, ns)), energy=np.empty((c, ns)),
+                       move_stat=np.empty((c, ns), dtype=np.uint8),
+                       ssf=np.empty((c, ns, m, 3)) if m else None)
+        out['accept_rate'] = np.empty(c)
+        if sums:
+            out['sum_energy'] = np.empty((c, 2))
+            out['sum_ssf'] = np.empty((c, m, 3)) if m else None
+        rc = self._L.qmcb_vmc_run_block(
+            self._h, ns, ptr(out.get('lnpsi')), ptr(out.get('energy')),
+            ptr(out.get('move_stat')), ptr(out.get('ssf')),
+            ptr(out['accept_rate']), ptr(out.get('sum_energy')),
+            ptr(out.get('sum_ssf')))
+        self._check(rc, 'qmcb_vmc_run_block')
+        return out
+
+    def vmc_get_state(self):
+        c = self._vmc_chains
+        confs, ln = np.empty((c, 2, self.nop)), np.empty(c)
+        rc = self._L.qmcb_vmc_get_state(self._h, ptr(confs), ptr(ln))
+        self._check(rc, 'qmcb_vmc_get_state')
+        return confs, ln

@@ -1,0 +1,124 @@
+"""GPU parity tests: the CUDA engine, through the C ABI, against (a) outputs
+of the live reference frozen in tests/golden/ and (b) the C oracle on the same
+seeded inputs.  Tolerance: 1e-12 relative (BASELINE.json north_star); drift in
+max-norm."""
+import numpy as np
+import pytest
+
+from conftest import golden, golden_names, maxnorm_err, rel_err, scaled_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+@pytest.fixture(scope='module')
+def eng_mod():
+    from phd_qmclib_b200 import engine
+    return engine
+
+
+@pytest.mark.parametrize('name', golden_names('model_'))
+def test_model_eval_vs_reference(eng_mod, name):
+    g = golden(name)
+    with eng_mod.Engine((g['params'][:12], g['params'][12:19],
+                         g['params'][19:])) as eng:
+        o = eng.model_eval(g['confs'])
+    assert scaled_err(o['lnpsi'], g['lnpsi']) < TOL
+    assert scaled_err(o['energy'], g['energy']) < TOL
+    assert maxnorm_err(o['drift'], g['drift']) < TOL
+
+
+@pytest.mark.parametrize('name,nconf', [('lat_n100', 3000), ('lat_n50', 5000),
+                                        ('odd_n7', 4000), ('frac_n21', 2000),
+                                        ('deep_n200', 300)])
+def test_model_eval_vs_oracle_bulk(eng_mod, oracle, name, nconf):
+    g = golden('model_' + name + '.npz')
+    p = g['params']
+    nop, size = int(p[3]), float(p[4])
+    rng = np.random.default_rng(7)
+    confs = np.zeros((nconf, 2, nop))
+    confs[:, 0] = rng.random((nconf, nop)) * size
+    ref = oracle.model_eval(p, confs)
+    with eng_mod.Engine((p[:12], p[12:19], p[19:])) as eng:
+        o = eng.model_eval(confs)
+    assert scaled_err(o['lnpsi'], ref['lnpsi']) < TOL
+    assert scaled_err(o['energy'], ref['energy']) < TOL
+    assert maxnorm_err(o['drift'], ref['drift']) < TOL
+
+
+def _run_both(eng_mod, oracle, p, ini, wmax, target, dt, nwc, seed, nts,
+              nblocks, energy_mode=0):
+    size = float(p[4])
+    st = oracle.DMCState(p, ini, wmax)
+    eng = eng_mod.Engine((p[:12], p[12:19], p[19:]))
+    dp = eng.dmc_params(dt, wmax, target, nwc, seed, 0.0, size,
+                        energy_mode=energy_mode)
+    eng.dmc_init(dp, ini)
+    res = []
+    for _ in range(nblocks):
+        a = st.run_block(seed, dt, target, nwc, nts, 0.0, size,
+                         energy_mode=energy_mode)
+        b = eng.dmc_run_block(nts)
+        res.append((a, b))
+    return st, eng, res
+
+
+@pytest.mark.parametrize('name,n_ini,wmax,nts', [
+    ('ll_n16', 48, 64, 8), ('lat_n50', 40, 56, 6), ('odd_n7', 64, 96, 8),
+    ('defects_n20', 32, 48, 6), ('lat_n100', 24, 32, 4),
+    ('strong_n10', 40, 64, 6)])
+@pytest.mark.parametrize('energy_mode', [0, 1])
+def test_dmc_blocks_vs_oracle(eng_mod, oracle, name, n_ini, wmax, nts,
+                              energy_mode):
+    """Same seed, same Philox streams: branching decisions must be identical
+    and every per-step series must agree to rounding."""
+    g = golden('model_' + name + '.npz')
+    p = g['params']
+    nop, size = int(p[3]), float(p[4])
+    rng = np.random.default_rng(3)
+    ini = np.zeros((n_ini, 2, nop))
+    ini[:, 0] = rng.random((n_ini, nop)) * size
+    st, eng, res = _run_both(eng_mod, oracle, p, ini, wmax, n_ini, 1e-3,
+                             0.125, 42, nts, 2, energy_mode)
+    for a, b in res:
+        assert np.array_equal(a['num_walkers'], b['num_walkers'])
+        for k in ('energy', 'weight', 'ref_energy', 'accum_energy'):
+            assert rel_err(b[k], a[k]) < 1e-10, k
+    s = eng.dmc_get_state()
+    nw = st.num_walkers
+    assert int(s['scalars'].num_walkers) == nw
+    assert np.array_equal(s['cloning_ref'][:nw], st.ref[:nw])
+    assert np.array_equal(s['mask'], st.act['mask'])
+    assert np.allclose(s['confs'][:nw, 0], st.act['confs'][:nw, 0],
+                       rtol=0, atol=1e-9)
+    assert rel_err(s['energy'][:nw], st.act['energy'][:nw]) < 1e-9
+    nx = eng.dmc_get_next()
+    assert np.allclose(nx['confs'][:, 0], st.prev['confs'][:nw, 0], rtol=0,
+                       atol=1e-9)
+    assert maxnorm_err(nx['confs'][:, 1], st.prev['confs'][:nw, 1]) < 1e-8
+    assert rel_err(nx['weight'], st.prev['weight'][:nw]) < 1e-9
+    assert np.allclose(nx['slot_energy'], st.act['energy'], rtol=1e-9,
+                       atol=1e-9)
+    eng.close()
+
+
+def test_dmc_capacity_hit(eng_mod, oracle):
+    """Capacity truncation (quirk Q8) follows the reference's order."""
+    g = golden('model_ll_n16.npz')
+    p = g['params']
+    rng = np.random.default_rng(5)
+    ini = np.zeros((30, 2, 16))
+    ini[:, 0] = rng.random((30, 16)) * 16
+    # a far-too-low reference energy makes the population explode
+    st = oracle.DMCState(p, ini, 40, ref_energy=400.0)
+    eng = eng_mod.Engine((p[:12], p[12:19], p[19:]))
+    dp = eng.dmc_params(5e-3, 40, 30, 0.0, 9, 0.0, 16.0)
+    eng.dmc_init(dp, ini, ref_energy=400.0)
+    a = st.run_block(9, 5e-3, 30, 0.0, 4, 0.0, 16.0)
+    b = eng.dmc_run_block(4)
+    assert a['num_walkers'].max() == 40
+    assert np.array_equal(a['num_walkers'], b['num_walkers'])
+    assert rel_err(b['energy'], a['energy']) < 1e-10
+    assert eng.dmc_scalars().capacity_hits > 0
+    eng.close()
