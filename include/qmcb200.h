@@ -203,6 +203,19 @@ QMCB_API int qmcb_last_block_stats(qmcb_handle *h, double *total_ms,
  * per thread, all SMs), in TFLOP/s -- the fp64 roofline denominator that
  * MEASURED_PEAKS.json lacks.  ms (may be NULL) = best kernel time. */
 QMCB_API int qmcb_measure_fp64_peak(int device, double *tflops, double *ms);
+/* Same kernel launched back to back for `seconds` of wall time: the rate the
+ * FP64 pipe sustains under the power cap (denominator for a kernel timed
+ * inside a long step). */
+QMCB_API int qmcb_measure_fp64_sustained(int device, double seconds,
+                                         double *tflops);
+
+/* The engine's CUDA stream (a cudaStream_t), so that a caller can bracket
+ * calls with its own events on the launching stream. */
+QMCB_API void *qmcb_stream(qmcb_handle *h);
+/* Page-locked host buffers for the host-pointer entry points (copies from
+ * pageable memory are staged by the driver and are several times slower). */
+QMCB_API void *qmcb_host_alloc(int64_t bytes);
+QMCB_API void qmcb_host_free(void *p);
 
 /* ---- multi-GPU (one process per GPU) ------------------------------------ */
 /* 128-byte NCCL unique id, made on rank 0 and broadcast by the caller's own

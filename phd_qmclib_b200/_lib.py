@@ -19,7 +19,8 @@ SYMBOLS = [
     'qmcb_dmc_get_state', 'qmcb_dmc_get_next', 'qmcb_set_profiling',
     'qmcb_last_block_stats', 'qmcb_measure_fp64_peak', 'qmcb_comm_unique_id', 'qmcb_comm_init',
     'qmcb_dmc_rebalance', 'qmcb_vmc_init', 'qmcb_vmc_run_block',
-    'qmcb_vmc_get_state',
+    'qmcb_vmc_get_state', 'qmcb_measure_fp64_sustained', 'qmcb_stream',
+    'qmcb_host_alloc', 'qmcb_host_free',
 ]
 
 
@@ -99,6 +100,13 @@ def load():
     L.qmcb_last_block_stats.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl),
                                         C.POINTER(i64)]
     L.qmcb_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(dbl), C.POINTER(dbl)]
+    L.qmcb_measure_fp64_sustained.argtypes = [C.c_int, dbl, C.POINTER(dbl)]
+    L.qmcb_stream.argtypes = [vp]
+    L.qmcb_stream.restype = vp
+    L.qmcb_host_alloc.argtypes = [i64]
+    L.qmcb_host_alloc.restype = vp
+    L.qmcb_host_free.argtypes = [vp]
+    L.qmcb_host_free.restype = None
     L.qmcb_comm_unique_id.argtypes = [vp]
     L.qmcb_comm_init.argtypes = [vp, vp, i32, i32]
     L.qmcb_dmc_rebalance.argtypes = [vp, C.POINTER(i64)]
@@ -107,7 +115,8 @@ def load():
     L.qmcb_vmc_get_state.argtypes = [vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
-        if name not in ('qmcb_destroy', 'qmcb_last_error', 'qmcb_version'):
+        if name not in ('qmcb_destroy', 'qmcb_last_error', 'qmcb_version',
+                        'qmcb_stream', 'qmcb_host_alloc', 'qmcb_host_free'):
             fn.restype = C.c_int
     _lib = L
     return L

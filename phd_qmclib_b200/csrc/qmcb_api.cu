@@ -5,6 +5,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>       // types and prototypes only: the library is dlopen'ed
+
 #include "../../include/qmcb200.h"
 #include "qmcb_kernels.cuh"
 
@@ -19,6 +22,57 @@ struct Timer {
 };
 
 }  // namespace
+
+// NCCL entry points, resolved at run time so that libqmcb200.so loads (and its
+// single-GPU paths run) on a box without NCCL.  Inside a torch process the
+// soname resolves to the NCCL torch already mapped.
+struct NcclApi {
+    void *dl = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    std::string err;
+};
+
+static NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.dl ? &api : nullptr;
+    tried = true;
+    const char *env = getenv("QMCB_NCCL_LIB");
+    const char *names[] = {env, "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        if (!n || !*n) continue;
+        api.dl = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.dl) break;
+    }
+    if (!api.dl) {
+        api.err = "libnccl.so.2 not loadable (set QMCB_NCCL_LIB)";
+        return nullptr;
+    }
+#define QMCB_NCCL_SYM(name)                                                  \
+    api.name = (decltype(api.name)) dlsym(api.dl, "nccl" #name);             \
+    if (!api.name) {                                                         \
+        api.err = "nccl" #name " missing";                                   \
+        api.dl = nullptr;                                                    \
+        return nullptr;                                                      \
+    }
+    QMCB_NCCL_SYM(GetUniqueId) QMCB_NCCL_SYM(CommInitRank)
+    QMCB_NCCL_SYM(CommDestroy) QMCB_NCCL_SYM(AllReduce)
+    QMCB_NCCL_SYM(AllGather) QMCB_NCCL_SYM(Send) QMCB_NCCL_SYM(Recv)
+    QMCB_NCCL_SYM(GroupStart) QMCB_NCCL_SYM(GroupEnd)
+    QMCB_NCCL_SYM(GetErrorString)
+#undef QMCB_NCCL_SYM
+    return &api;
+}
 
 struct qmcb_handle {
     int device = 0;
@@ -48,6 +102,11 @@ struct qmcb_handle {
     bool profile_steps = false;
     double last_total_ms = 0.0, last_step_ms = 0.0;
     long long last_launches = 0;
+
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0;
+    long long *d_counts = nullptr;      // [world] live walkers per rank
 };
 
 #define CUDA_TRY(h, expr)                                                    \
@@ -59,6 +118,18 @@ struct qmcb_handle {
                      __FILE__, __LINE__, cudaGetErrorString(_e));            \
             (h)->err = _b;                                                   \
             return QMCB_ERR_CUDA;                                            \
+        }                                                                    \
+    } while (0)
+
+#define NCCL_TRY(h, expr)                                                    \
+    do {                                                                     \
+        ncclResult_t _r = (expr);                                            \
+        if (_r != ncclSuccess) {                                             \
+            char _b[512];                                                    \
+            snprintf(_b, sizeof _b, "%s failed at %s:%d: %s", #expr,         \
+                     __FILE__, __LINE__, nccl_api()->GetErrorString(_r));    \
+            (h)->err = _b;                                                   \
+            return QMCB_ERR_NCCL;                                            \
         }                                                                    \
     } while (0)
 
@@ -217,7 +288,6 @@ void free_dmc(qmcb_handle *h)
 int alloc_dmc(qmcb_handle *h, const qmcb_dmc_params *p,
               long long slot_offset)
 {
-    free_dmc(h);
     if (p->max_num_walkers < 1 || p->target_num_walkers < 1)
         FAIL(h, QMCB_ERR_INVALID, "max/target_num_walkers must be >= 1");
     long long cap = p->local_capacity > 0 ? p->local_capacity
@@ -226,32 +296,41 @@ int alloc_dmc(qmcb_handle *h, const qmcb_dmc_params *p,
     if (!(p->time_step > 0)) FAIL(h, QMCB_ERR_INVALID, "time_step must be > 0");
     if (!(p->upper_bound > p->lower_bound))
         FAIL(h, QMCB_ERR_INVALID, "upper_bound must exceed lower_bound");
-    h->dp = *p;
     DmcBufs &B = h->B;
-    B.cap = (int) cap;
-    B.nblk = (int) ((cap + BR_TILE - 1) / BR_TILE);
     const int N = h->M.nop;
     size_t cb = (size_t) cap * 2 * N * sizeof(double);
+    // a restart with the same capacity keeps the device allocation
+    const bool reuse = B.confs[0] != nullptr && B.cap == (int) cap;
+    if (!reuse) {
+        free_dmc(h);
+        B.cap = (int) cap;
+        B.nblk = (int) ((cap + BR_TILE - 1) / BR_TILE);
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(h, cudaMalloc(&B.confs[i], cb));
+            CUDA_TRY(h, cudaMalloc(&B.energy[i], cap * sizeof(double)));
+            CUDA_TRY(h, cudaMalloc(&B.weight[i], cap * sizeof(double)));
+        }
+        CUDA_TRY(h, cudaMalloc(&B.slot_energy, cap * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc(&B.ref, cap * sizeof(int)));
+        CUDA_TRY(h, cudaMalloc(&B.cnt, cap * sizeof(int)));
+        CUDA_TRY(h, cudaMalloc(&B.blocksum, B.nblk * sizeof(long long)));
+        CUDA_TRY(h, cudaMalloc(&B.blockoff, B.nblk * sizeof(long long)));
+        CUDA_TRY(h, cudaMalloc(&B.epart, B.nblk * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc(&B.ctl, sizeof(DmcCtl)));
+        for (int i = 0; i < 2; ++i)
+            CUDA_TRY(h, cudaMemsetAsync(B.confs[i], 0, cb, h->stream));
+    }
+    h->dmc_ready = false;
+    h->dp = *p;
     for (int i = 0; i < 2; ++i) {
-        CUDA_TRY(h, cudaMalloc(&B.confs[i], cb));
-        CUDA_TRY(h, cudaMalloc(&B.energy[i], cap * sizeof(double)));
-        CUDA_TRY(h, cudaMalloc(&B.weight[i], cap * sizeof(double)));
-        CUDA_TRY(h, cudaMemsetAsync(B.confs[i], 0, cb, h->stream));
         CUDA_TRY(h, cudaMemsetAsync(B.energy[i], 0, cap * sizeof(double),
                                     h->stream));
         CUDA_TRY(h, cudaMemsetAsync(B.weight[i], 0, cap * sizeof(double),
                                     h->stream));
     }
-    CUDA_TRY(h, cudaMalloc(&B.slot_energy, cap * sizeof(double)));
     CUDA_TRY(h, cudaMemsetAsync(B.slot_energy, 0, cap * sizeof(double),
                                 h->stream));
-    CUDA_TRY(h, cudaMalloc(&B.ref, cap * sizeof(int)));
     CUDA_TRY(h, cudaMemsetAsync(B.ref, 0, cap * sizeof(int), h->stream));
-    CUDA_TRY(h, cudaMalloc(&B.cnt, cap * sizeof(int)));
-    CUDA_TRY(h, cudaMalloc(&B.blocksum, B.nblk * sizeof(long long)));
-    CUDA_TRY(h, cudaMalloc(&B.blockoff, B.nblk * sizeof(long long)));
-    CUDA_TRY(h, cudaMalloc(&B.epart, B.nblk * sizeof(double)));
-    CUDA_TRY(h, cudaMalloc(&B.ctl, sizeof(DmcCtl)));
     CUDA_TRY(h, cudaMemsetAsync(B.ctl, 0, sizeof(DmcCtl), h->stream));
 
     DmcConsts &C = h->C;
@@ -386,6 +465,8 @@ void qmcb_destroy(qmcb_handle *h)
     cudaStreamSynchronize(h->stream);
     free_dmc(h);
     cudaFree(h->d_scratch);
+    cudaFree(h->d_counts);
+    if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
     for (auto ev : h->step_ev) cudaEventDestroy(ev);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -587,6 +668,12 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
         branch_scan_kernel<<<1, BR_THREADS, 0, h->stream>>>(B);
         branch_fill_kernel<<<B.nblk, BR_THREADS, 0, h->stream>>>(B);
         dmc_local_sum_kernel<<<1, BR_THREADS, 0, h->stream>>>(B);
+        if (h->comm)
+            // population control needs the GLOBAL {sum E, W}
+            // (qmc_base/dmc.py:758-771); 16 bytes, in place
+            NCCL_TRY(h, nccl_api()->AllReduce(
+                            (const void *) (B.ctl_red), (void *) (B.ctl_red),
+                            2, ncclDouble, ncclSum, h->comm, h->stream));
         if (h->profile_steps)
             CUDA_TRY(h, cudaEventRecord(h->step_ev[2 * i], h->stream));
         dmc_step_kernel<<<step_grid, g.nthreads, g.smem_bytes, h->stream>>>(
@@ -598,7 +685,7 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     h->step_host += nts;
-    h->last_launches = 6 * nts;
+    h->last_launches = (6 + (h->comm ? 1 : 0)) * nts;
     if (energy)
         CUDA_TRY(h, cudaMemcpyAsync(energy, L.energy, nts * sizeof(double),
                                     cudaMemcpyDeviceToHost, h->stream));
@@ -771,18 +858,207 @@ int qmcb_measure_fp64_peak(int device, double *tflops, double *ms_out)
     return QMCB_OK;
 }
 
-int qmcb_comm_unique_id(uint8_t *) { return QMCB_ERR_NCCL; }
-
-int qmcb_comm_init(qmcb_handle *h, const uint8_t *, int32_t, int32_t)
+int qmcb_measure_fp64_sustained(int device, double seconds, double *tflops)
 {
-    if (!h) return QMCB_ERR_INVALID;
-    FAIL(h, QMCB_ERR_NCCL, "qmcb_comm_init: not implemented yet");
+    if (!tflops || !(seconds > 0)) return QMCB_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return QMCB_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return QMCB_ERR_CUDA;
+    const int grid = prop.multiProcessorCount * 8, iters = 4096;
+    double *d = nullptr;
+    if (cudaMalloc(&d, (size_t) grid * 256 * sizeof(double)) != cudaSuccess)
+        return QMCB_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    // one launch to learn the duration, then a fixed count back to back
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<grid, 256>>>(d, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms1 = 0.f;
+    cudaEventElapsedTime(&ms1, e0, e1);
+    int n = (int) (seconds * 1e3 / (ms1 > 0.01f ? ms1 : 0.01f));
+    if (n < 4) n = 4;
+    if (n > 100000) n = 100000;
+    cudaEventRecord(e0);
+    for (int i = 0; i < n; ++i)
+        fp64_peak_kernel<<<grid, 256>>>(d, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    if (e != cudaSuccess || !(ms > 0)) return QMCB_ERR_CUDA;
+    double flops = 2.0 * 64.0 * iters * (double) grid * 256.0 * n;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    return QMCB_OK;
 }
 
-int qmcb_dmc_rebalance(qmcb_handle *h, int64_t *)
+void *qmcb_stream(qmcb_handle *h) { return h ? (void *) h->stream : nullptr; }
+
+void *qmcb_host_alloc(int64_t bytes)
+{
+    void *p = nullptr;
+    if (bytes <= 0) return nullptr;
+    if (cudaHostAlloc(&p, (size_t) bytes, cudaHostAllocDefault) != cudaSuccess)
+        return nullptr;
+    return p;
+}
+
+void qmcb_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int qmcb_comm_unique_id(uint8_t *id)
+{
+    NcclApi *api = nccl_api();
+    if (!api || !id) return QMCB_ERR_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId uid;
+    if (api->GetUniqueId(&uid) != ncclSuccess) return QMCB_ERR_NCCL;
+    memcpy(id, &uid, sizeof uid);
+    return QMCB_OK;
+}
+
+int qmcb_comm_init(qmcb_handle *h, const uint8_t *id, int32_t world_size,
+                   int32_t rank)
 {
     if (!h) return QMCB_ERR_INVALID;
-    FAIL(h, QMCB_ERR_NCCL, "qmcb_dmc_rebalance: not implemented yet");
+    if (!id || world_size < 1 || rank < 0 || rank >= world_size)
+        FAIL(h, QMCB_ERR_INVALID, "bad communicator arguments");
+    NcclApi *api = nccl_api();
+    if (!api) FAIL(h, QMCB_ERR_NCCL, "NCCL not loadable: libnccl.so.2");
+    if (h->comm) FAIL(h, QMCB_ERR_STATE, "communicator already initialised");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    NCCL_TRY(h, api->CommInitRank(&h->comm, world_size, uid, rank));
+    h->world = world_size;
+    h->rank = rank;
+    CUDA_TRY(h, cudaMalloc(&h->d_counts, world_size * sizeof(long long)));
+    return QMCB_OK;
+}
+
+// Order-preserving rebalance.  The global ensemble is the
+// concatenation of the ranks' live walkers; the new partition gives rank r
+// the global range [T r / R, T (r + 1) / R).  Every rank sends the parts of
+// its current range that fall into other ranks' new ranges and receives the
+// parts of its new range that others hold -- with fluctuating populations
+// these are thin slices at the boundaries with the ring neighbours.  Works on
+// the evolved population the next step will branch from.
+int qmcb_dmc_rebalance(qmcb_handle *h, int64_t *moved)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (moved) *moved = 0;
+    if (!h->dmc_ready) FAIL(h, QMCB_ERR_STATE, "qmcb_dmc_init not called");
+    if (!h->comm || h->world == 1) return QMCB_OK;
+    NcclApi *api = nccl_api();
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    DmcBufs &B = h->B;
+    const int R = h->world, me = h->rank, N = h->M.nop;
+    DmcCtl ctl;
+    int rc = read_ctl(h, ctl);
+    if (rc) return rc;
+    const int par = (int) (ctl.step & 1);
+    long long mine = ctl.W_prev;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_counts + me, &mine, sizeof mine,
+                                cudaMemcpyHostToDevice, h->stream));
+    NCCL_TRY(h, api->AllGather(h->d_counts + me, h->d_counts, 1, ncclInt64,
+                               h->comm, h->stream));
+    std::vector<long long> cnt(R);
+    CUDA_TRY(h, cudaMemcpyAsync(cnt.data(), h->d_counts,
+                                R * sizeof(long long), cudaMemcpyDeviceToHost,
+                                h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    std::vector<long long> cur0(R + 1, 0), new0(R + 1, 0);
+    for (int r = 0; r < R; ++r) cur0[r + 1] = cur0[r] + cnt[r];
+    const long long T = cur0[R];
+    for (int r = 0; r <= R; ++r) new0[r] = T * r / R;
+    const long long new_n = new0[me + 1] - new0[me];
+    if (new_n > B.cap) FAIL(h, QMCB_ERR_STATE, "rebalance exceeds capacity");
+    bool any = false;
+    for (int r = 0; r < R; ++r) any = any || cur0[r] != new0[r];
+    if (!any) return QMCB_OK;
+
+    // staging: [new_n] x (confs, energy, weight)
+    const size_t row = (size_t) 2 * N;
+    size_t need = (size_t) new_n * (row + 2) * sizeof(double);
+    rc = ensure_scratch(h, need);
+    if (rc) return rc;
+    double *s_confs = h->d_scratch;
+    double *s_energy = s_confs + (size_t) new_n * row;
+    double *s_weight = s_energy + new_n;
+    long long sent = 0;
+    auto overlap = [](long long a0, long long a1, long long b0, long long b1,
+                      long long &lo, long long &hi) {
+        lo = a0 > b0 ? a0 : b0;
+        hi = a1 < b1 ? a1 : b1;
+        return hi > lo;
+    };
+    NCCL_TRY(h, api->GroupStart());
+    for (int p = 0; p < R; ++p) {
+        long long lo, hi;
+        // my current walkers that p will own
+        if (overlap(cur0[me], cur0[me + 1], new0[p], new0[p + 1], lo, hi)) {
+            long long src = lo - cur0[me], n = hi - lo;
+            if (p == me) {
+                long long dst = lo - new0[me];
+                CUDA_TRY(h, cudaMemcpyAsync(
+                                s_confs + dst * row,
+                                B.confs[par] + src * row,
+                                n * row * sizeof(double),
+                                cudaMemcpyDeviceToDevice, h->stream));
+                CUDA_TRY(h, cudaMemcpyAsync(s_energy + dst,
+                                            B.energy[par] + src,
+                                            n * sizeof(double),
+                                            cudaMemcpyDeviceToDevice,
+                                            h->stream));
+                CUDA_TRY(h, cudaMemcpyAsync(s_weight + dst,
+                                            B.weight[par] + src,
+                                            n * sizeof(double),
+                                            cudaMemcpyDeviceToDevice,
+                                            h->stream));
+            } else {
+                NCCL_TRY(h, api->Send(B.confs[par] + src * row, n * row,
+                                      ncclDouble, p, h->comm, h->stream));
+                NCCL_TRY(h, api->Send(B.energy[par] + src, n, ncclDouble, p,
+                                      h->comm, h->stream));
+                NCCL_TRY(h, api->Send(B.weight[par] + src, n, ncclDouble, p,
+                                      h->comm, h->stream));
+                sent += n;
+            }
+        }
+        // walkers of p that I will own
+        if (p != me
+            && overlap(cur0[p], cur0[p + 1], new0[me], new0[me + 1], lo, hi)) {
+            long long dst = lo - new0[me], n = hi - lo;
+            NCCL_TRY(h, api->Recv(s_confs + dst * row, n * row, ncclDouble, p,
+                                  h->comm, h->stream));
+            NCCL_TRY(h, api->Recv(s_energy + dst, n, ncclDouble, p, h->comm,
+                                  h->stream));
+            NCCL_TRY(h, api->Recv(s_weight + dst, n, ncclDouble, p, h->comm,
+                                  h->stream));
+        }
+    }
+    NCCL_TRY(h, api->GroupEnd());
+    CUDA_TRY(h, cudaMemcpyAsync(B.confs[par], s_confs,
+                                new_n * row * sizeof(double),
+                                cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(B.energy[par], s_energy,
+                                new_n * sizeof(double),
+                                cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(B.weight[par], s_weight,
+                                new_n * sizeof(double),
+                                cudaMemcpyDeviceToDevice, h->stream));
+    int w = (int) new_n;
+    CUDA_TRY(h, cudaMemcpyAsync(&B.ctl->W_prev, &w, sizeof w,
+                                cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (moved) *moved = sent;
+    return QMCB_OK;
 }
 
 int qmcb_vmc_init(qmcb_handle *h, const qmcb_vmc_params *, const double *,

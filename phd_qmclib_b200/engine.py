@@ -10,11 +10,63 @@ from . import _lib
 from ._lib import DMCParams, EngineError, StateScalars, VMCParams, ptr
 from .model import param_block
 
-__all__ = ['Engine', 'EngineError']
+__all__ = ['Engine', 'EngineError', 'pinned_empty', 'measure_fp64_peak']
 
 
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class _PinnedBlock:
+    """Owner of one cudaHostAlloc block (freed when the last view dies)."""
+
+    def __init__(self, nbytes):
+        self._L = _lib.load()
+        self.ptr = self._L.qmcb_host_alloc(nbytes)
+        if not self.ptr:
+            raise EngineError(f'qmcb_host_alloc({nbytes}) failed')
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            self._L.qmcb_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """A page-locked numpy array (for fast host<->device copies)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    block = _PinnedBlock(max(n * dtype.itemsize, 1))
+    buf = (C.c_byte * block.nbytes).from_address(block.ptr)
+    buf._owner = block
+    a = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    return a
+
+
+def measure_fp64_peak(device=0, sustained_seconds=0.0):
+    """DFMA throughput of ``device`` in TFLOP/s: burst (best single launch)
+    or, with ``sustained_seconds`` > 0, back-to-back launches for that long."""
+    L = _lib.load()
+    tf, ms = C.c_double(), C.c_double()
+    if sustained_seconds > 0:
+        rc = L.qmcb_measure_fp64_sustained(device, sustained_seconds,
+                                           C.byref(tf))
+    else:
+        rc = L.qmcb_measure_fp64_peak(device, C.byref(tf), C.byref(ms))
+    if rc != 0:
+        raise EngineError(f'fp64 peak measurement failed ({rc})')
+    return tf.value
+
+
+def comm_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    rc = _lib.load().qmcb_comm_unique_id(buf)
+    if rc != 0:
+        raise EngineError(f'qmcb_comm_unique_id failed ({rc}): NCCL not '
+                          f'loadable')
+    return bytes(buf)
 
 
 class Engine:
@@ -61,6 +113,11 @@ class Engine:
     @property
     def handle(self):
         return self._h
+
+    @property
+    def stream(self):
+        """The engine's cudaStream_t as an integer."""
+        return self._L.qmcb_stream(self._h) or 0
 
     # -- fixed-configuration evaluation ------------------------------------
     def model_eval(self, confs, want=('lnpsi', 'energy', 'drift')):
@@ -208,6 +265,35 @@ class Engine:
         self._check(rc, 'qmcb_dmc_get_next')
         out['scalars'] = sc
         return out
+
+    def dmc_get_next_into(self, confs, energy, weight, slot_energy):
+        """Copy the evolved population into caller-owned (ideally pinned)
+        arrays sized for the capacity; returns the scalars."""
+        sc = StateScalars()
+        rc = self._L.qmcb_dmc_get_next(
+            self._h, ptr(confs), ptr(energy), ptr(weight), ptr(slot_energy),
+            C.byref(sc))
+        self._check(rc, 'qmcb_dmc_get_next')
+        return sc
+
+    # -- multi-GPU ----------------------------------------------------------
+    def comm_init(self, unique_id: bytes, world_size: int, rank: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        rc = self._L.qmcb_comm_init(self._h, buf, world_size, rank)
+        self._check(rc, 'qmcb_comm_init')
+
+    def comm_init_torch(self, dist, rank, world_size):
+        """Create the NCCL communicator, shipping the unique id through an
+        initialised ``torch.distributed`` process group (plumbing only)."""
+        uid = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        self.comm_init(uid[0], world_size, rank)
+
+    def dmc_rebalance(self):
+        moved = C.c_int64()
+        rc = self._L.qmcb_dmc_rebalance(self._h, C.byref(moved))
+        self._check(rc, 'qmcb_dmc_rebalance')
+        return moved.value
 
     def set_profiling(self, on=True):
         self._check(self._L.qmcb_set_profiling(self._h, int(on)),
