@@ -1,5 +1,8 @@
 // C ABI of libqmcb200.so (see include/qmcb200.h).
 #include <cmath>
+#include <cstddef>
+#include <cstdlib>
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -174,53 +177,74 @@ bool build_model(const qmcb_model_params &p, DevModel &M, std::string &err)
     double rm = std::fabs(t[1]);
     double k2 = t[2], beta = t[3], r_off = t[4], am = t[5];
     M.k2 = k2; M.beta = beta;
+    M.k1_over_pi = M.k1 / M_PI;
+    M.k2_over_pi = k2 / M_PI;
     M.ln_am = std::log(std::fabs(am));
-    M.s_m = std::sin(M_PI * rm / M.L);
-    if (rm >= 0.5 * M.L) M.s_m = 1.0;
-    M.A_far = (M_PI / M.L) * beta;
-    M.B_far = (M_PI / M.L) * (M_PI / M.L) * beta;
-    M.A_near = -k2;
-    M.B_near = k2 * k2;
-    double phi = k2 * r_off;
-    M.cps0 = std::cos(phi); M.sps0 = std::sin(phi);
-    M.cps1 = std::cos(phi - k2 * M.L); M.sps1 = std::sin(phi - k2 * M.L);
+    double s_m = std::sin(M_PI * rm / M.L);
+    if (rm >= 0.5 * M.L) s_m = 1.0;
+    if (!M.is_ideal && !(k2 > 0 && beta > 0)) {
+        err = "two-body parameters k2 and beta must be positive";
+        return false;
+    }
+    // near-branch units (qmcb_dev.cuh): drift in -k2, kinetic in k2^2
+    double gam = M.is_ideal ? 1.0 : (M_PI / M.L) * std::sqrt(beta) / k2;
+    M.inv_gam = 1.0 / gam;
+    M.mu_over_gam = M.is_ideal ? 0.0 : -(M_PI / M.L) * beta / (k2 * gam);
+    M.s_m_scaled = s_m / gam;
+    M.ln_gam = std::log(gam);
+    M.drift_unit = -k2;
+    M.kin_unit = k2 * k2;
+    double psi0 = k2 * r_off, psi1 = k2 * r_off - k2 * M.L;
+    M.cpsi[0] = std::cos(psi0); M.spsi[0] = std::sin(psi0);
+    M.cpsi[1] = std::cos(psi1); M.spsi[1] = std::sin(psi1);
     return true;
 }
 
 // CTA shape: threads per walker = nb; pack G walkers into a CTA so that few
-// lanes idle, keeping >= ~10 resident warps per SM where shared memory and
+// lanes idle, and pick the number of column-sum slots kept in shared memory
+// (kc) so that shared memory does not cap the resident warps below what the
 // registers allow.
 bool choose_geom(const DevModel &M, int max_smem, GroupGeom &g,
                  std::string &err)
 {
-    const int regs_per_thread = 168;
+    const int regs_per_thread = 128;
     double best = -1.0;
-    const int nbp = M.nb;
+    const int nbp = M.nb + (M.nb & 1);
+    const int kfull = M.kmax + 1;
+    const char *env_kc = getenv("QMCB_KC");
+    const char *env_nt = getenv("QMCB_NT");
     for (int nt = 64; nt <= 256; nt += 32) {
+        if (env_nt && atoi(env_nt) != nt) continue;
         int G = nt / M.nb;
         if (G < 1) continue;
-        int bytes = 0;
-        for (; G >= 1; --G) {
-            bytes = group_smem_doubles(G, nbp, M.kmax + 1) * 8;
-            if (bytes <= max_smem) break;
-        }
-        if (G < 1) continue;
         double eff = (double) (G * M.nb) / nt;
-        int by_smem = (228 * 1024) / (bytes + 1024);
         int by_regs = 65536 / (regs_per_thread * nt);
         int by_thr = 2048 / nt;
-        int ctas = std::min(by_smem, std::min(by_regs, by_thr));
-        if (ctas < 1) ctas = 1;
-        double warps = ctas * nt / 32.0;
-        double score = eff * std::min(1.0, warps / 10.0);
-        if (score > best + 1e-9) {
-            best = score;
-            g.nthreads = nt; g.G = G; g.nbp = nbp; g.smem_bytes = bytes;
+        std::vector<int> kcs;
+        if (env_kc)
+            kcs.push_back(std::max(1, std::min(kfull, atoi(env_kc))));
+        else
+            for (int kc = kfull; kc >= 1; kc = (kc > 4 ? (kc + 1) / 2 : kc - 1))
+                kcs.push_back(kc);
+        for (int kc : kcs) {
+            int bytes = group_smem_doubles(G, nbp, kc) * 8;
+            if (bytes > max_smem) continue;
+            int by_smem = (228 * 1024) / (bytes + 1024);
+            int ctas = std::min(by_smem, std::min(by_regs, by_thr));
+            if (ctas < 1) continue;
+            double warps = ctas * nt / 32.0;
+            // every halving of kc costs two more CTA barriers per walker
+            double sync_pen = 1.0 - 0.004 * ((kfull + kc - 1) / kc - 1);
+            double score = eff * std::min(1.0, warps / 16.0) * sync_pen;
+            if (score > best + 1e-9) {
+                best = score;
+                g.nthreads = nt; g.G = G; g.nbp = nbp; g.kc = kc;
+                g.smem_bytes = bytes;
+            }
         }
     }
     if (best < 0) {
-        err = "boson_number too large for the shared-memory pair tables "
-              "(limit ~440 particles)";
+        err = "boson_number too large for the shared-memory pair tables";
         return false;
     }
     return true;
@@ -672,7 +696,9 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
             // population control needs the GLOBAL {sum E, W}
             // (qmc_base/dmc.py:758-771); 16 bytes, in place
             NCCL_TRY(h, nccl_api()->AllReduce(
-                            (const void *) (B.ctl_red), (void *) (B.ctl_red),
+                            (const void *) ((char *) B.ctl
+                                            + offsetof(DmcCtl, red)),
+                            (void *) ((char *) B.ctl + offsetof(DmcCtl, red)),
                             2, ncclDouble, ncclSum, h->comm, h->stream));
         if (h->profile_steps)
             CUDA_TRY(h, cudaEventRecord(h->step_ev[2 * i], h->stream));

@@ -10,16 +10,23 @@
 //
 // The arithmetic is NOT a transliteration.  With a_i = pi z_i / L and
 // u_i = k2 z_i tabulated once per particle (sin, cos), every pair term follows
-// from angle-addition identities, one reciprocal and no transcendental:
-//   far  (r >= r_m):  f2'/f2 * sgn = (pi/L) beta  cos(a_i-a_j)/sin(a_i-a_j)
-//                     -f2''/f2 + (f2'/f2)^2 = (pi/L)^2 beta / sin^2(a_i-a_j)
-//   near (r <  r_m):  theta = k2 r - k2 r_off,
-//                     f2'/f2 = -k2 tan(theta),
-//                     -f2''/f2 + (f2'/f2)^2 = k2^2 / cos^2(theta)
-// cot and 1/sin^2 have period L in z_i - z_j, so the far branch needs no
-// minimum-image step; the near branch folds the wrap and sgn(d) into a
-// rotation by a constant angle.  r < r_m <=> |sin(a_i - a_j)| < sin(pi r_m/L)
-// because r lies in [0, L/2].  Results agree with the reference to ~1e-15
+// from angle-addition identities, one reciprocal and no transcendental.  For
+// the pair (i, j), d = z_i - z_j, r = |d_min|, sigma = sgn(d_min):
+//   far  (r >= r_m):  sigma f2'/f2 = (pi/L) beta  cot(a_i - a_j)
+//                     -f2''/f2 + (f2'/f2)^2 = (pi/L)^2 beta / sin^2(a_i - a_j)
+//   near (r <  r_m):  sigma f2'/f2 = -k2 tan(u_i - u_j')
+//                     -f2''/f2 + (f2'/f2)^2 = k2^2 / cos^2(u_i - u_j')
+//     with u_j' = u_j + sigma psi_w, psi_0 = k2 r_off (|d| <= L/2),
+//     psi_1 = k2 r_off - k2 L (wrapped pair): the minimum-image fold and the
+//     sign of d become one of FOUR precomputed rotations of the column
+//     particle's (sin u_j, cos u_j), picked by the sign bits of
+//     sin(a_i - a_j) and cos(a_i - a_j).
+// cot and 1/sin^2 have period L in d, so the far branch needs no fold at all,
+// and r < r_m <=> |sin(a_i - a_j)| < sin(pi r_m / L) because r <= L/2.
+// Both branches are brought to the same units (the column tables of the far
+// branch are pre-scaled) so that one reciprocal yields
+//   t = num/den  (drift contribution / -k2)   and   1/den^2  (kinetic / k2^2)
+// with no per-pair constants.  Results agree with the reference to ~1e-15
 // relative (tests/), far inside the 1e-12 budget of the north star.
 #pragma once
 #include <cuda_runtime.h>
@@ -39,19 +46,25 @@ struct DevModel {
     double L, inv_L;
     // one-body (Kronig-Penney cell: well [0, za], barrier (za, 1))
     double za, zb, k1, kp1, e0, v0, vdef, ln_cf;
+    double k1_over_pi;
     // two-body
-    double s_m;                       // sin(pi r_m / L)
     double beta, ln_am, k2;
-    double A_far, B_far, A_near, B_near;
-    double cps0, sps0;                // cos/sin(k2 r_off)
-    double cps1, sps1;                // cos/sin(k2 r_off - k2 L)
+    double k2_over_pi;
+    double inv_gam;                   // 1/gamma_f, gamma_f = (pi/L) sqrt(beta)/k2
+    double mu_over_gam;               // -(pi/L) beta / (k2 gamma_f)
+    double s_m_scaled;                // sin(pi r_m / L) / gamma_f
+    double ln_gam;                    // ln gamma_f
+    double cpsi[2], spsi[2];          // cos/sin(psi_w)
+    double drift_unit;                // -k2
+    double kin_unit;                  // k2^2
 };
 
 // Launch geometry shared by every walker-group kernel.
 struct GroupGeom {
     int nthreads;       // CTA size (multiple of 32)
     int G;              // walkers per CTA
-    int nbp;            // padded row length of the shared tables (>= nb)
+    int nbp;            // padded row length of the shared tables (>= nb, even)
+    int kc;             // column-sum slots kept in shared memory at a time
     int smem_bytes;
 };
 
@@ -183,10 +196,9 @@ __device__ __forceinline__ OneBody one_body(const DevModel &M, double z)
         o.pot = defect ? M.vdef : M.v0;
         if (LN) o.lnf = log(cosh(arg));
     } else {                                        // well
-        double arg = M.k1 * (zc - 0.5 * M.za);
         double s, c;
-        sincos(arg, &s, &c);
-        o.ldz = -M.k1 * (s / c);
+        sincospi(M.k1_over_pi * (zc - 0.5 * M.za), &s, &c);
+        o.ldz = -M.k1 * (s * fast_rcp(c));
         o.kin = M.e0 + o.ldz * o.ldz;
         o.pot = 0.0;
         if (LN) o.lnf = M.ln_cf + log(fabs(c));
@@ -199,86 +211,57 @@ __device__ __forceinline__ void particle_tables(const DevModel &M, double z,
                                                 double &sa, double &ca,
                                                 double &su, double &cu)
 {
-    sincospi(z / M.L, &sa, &ca);
-    sincos(M.k2 * z, &su, &cu);
+    sincospi(z * M.inv_L, &sa, &ca);
+    sincospi(z * M.k2_over_pi, &su, &cu);
 }
 
 // ---------------------------------------------------------------------------
-// The pair term.  (i) is the row particle (this thread), (j) the column one.
-//   v  : contribution to F_i (and -v to F_j)
-//   kk : -f2''/f2 + (f2'/f2)^2 of the unordered pair
-//   far/near factor for ln|f2|: |sin(a_i-a_j)| (to the power beta) or
-//   |cos(theta)| (times a_m).
-// ---------------------------------------------------------------------------
-template <bool LN>
-__device__ __forceinline__ void pair_term(const DevModel &M,
-                                          double sa_i, double ca_i,
-                                          double su_i, double cu_i,
-                                          double sa_j, double ca_j,
-                                          double su_j, double cu_j,
-                                          double &v, double &kk,
-                                          double &ffar, double &fnear,
-                                          int &is_near)
-{
-    double Sa = fma(sa_i, ca_j, -(ca_i * sa_j));
-    double Ca = fma(ca_i, ca_j, sa_i * sa_j);
-    double Su = fma(su_i, cu_j, -(cu_i * su_j));
-    double Cu = fma(cu_i, cu_j, su_i * su_j);
-    bool near = fabs(Sa) < M.s_m;
-    int hiC = __double2hiint(Ca);
-    bool wrapped = hiC < 0;
-    int sgn = (__double2hiint(Sa) ^ hiC) & 0x80000000;       // sign(d_min)
-    double sSu = flip_sign(Su, sgn);
-    double cps = wrapped ? M.cps1 : M.cps0;
-    double sps = wrapped ? M.sps1 : M.sps0;
-    double S2 = fma(sSu, cps, -(Cu * sps));                  // sin(theta)
-    double C2 = fma(Cu, cps, sSu * sps);                     // cos(theta)
-    double num = near ? S2 : Ca;
-    double den = near ? C2 : Sa;
-    double A = near ? flip_sign(M.A_near, sgn) : M.A_far;
-    double B = near ? M.B_near : M.B_far;
-    double inv = fast_rcp(den);
-    v = (A * num) * inv;
-    kk = (B * inv) * inv;
-    if (LN) {
-        ffar = near ? 1.0 : fabs(Sa);
-        fnear = near ? fabs(C2) : 1.0;
-        is_near = near ? 1 : 0;
-    }
-}
-
-// ---------------------------------------------------------------------------
-// Shared-memory view of one CTA: G walkers, each with
-//   tab [4 arrays][4 particles-in-block][nbp blocks]   (sa, ca, su, cu)
-//   Q   [kmax+1 slots][4][nbp]   column partial sums of the drift
-//   red [2][nbp]                 per-thread partials of E_L and ln|Psi|
+// Shared-memory view of one CTA: G walkers, each with (nbp doubles per row)
+//   A1  [4][nbp] double2   (sin a_j, cos a_j) / gamma_f         far den
+//   A2  [4][nbp] double2   (sin a_j, cos a_j) mu_f / gamma_f    far num
+//   V   [4 variants][4][nbp] double2  (sin, cos)(u_j + sigma psi_w)
+//   Q   [kc][4][nbp]       column partial sums of the drift
+//   red [2][nbp]           per-thread partials of E_L and ln|Psi|
 // Particle p = 4 J + c is stored at [..][c][J]: the threads of a walker walk
-// J, so every access is unit-stride across lanes (no bank conflicts).
+// J, so accesses are unit-stride across lanes.  nbp is even, which makes the
+// variant stride a multiple of 128 bytes: lanes that pick different variants
+// still hit distinct banks.
 // ---------------------------------------------------------------------------
 struct GroupSmem {
     double *base;
-    int nbp, kslots;
+    int nbp, kc;
     __device__ __forceinline__ int walker_stride() const
     {
-        return (16 + 4 * kslots + 2) * nbp;
+        return (48 + 4 * kc + 2) * nbp;
     }
-    __device__ __forceinline__ double *tab(int g, int a, int c) const
+    __device__ __forceinline__ double2 *a1(int g, int c) const
     {
-        return base + g * walker_stride() + (a * 4 + c) * nbp;
+        return reinterpret_cast<double2 *>(base + g * walker_stride())
+               + c * nbp;
+    }
+    __device__ __forceinline__ double2 *a2(int g, int c) const
+    {
+        return reinterpret_cast<double2 *>(base + g * walker_stride()
+                                           + 8 * nbp) + c * nbp;
+    }
+    __device__ __forceinline__ double2 *var(int g, int v, int c) const
+    {
+        return reinterpret_cast<double2 *>(base + g * walker_stride()
+                                           + 16 * nbp) + (v * 4 + c) * nbp;
     }
     __device__ __forceinline__ double *q(int g, int k, int c) const
     {
-        return base + g * walker_stride() + (16 + k * 4 + c) * nbp;
+        return base + g * walker_stride() + (48 + k * 4 + c) * nbp;
     }
     __device__ __forceinline__ double *red(int g, int which) const
     {
-        return base + g * walker_stride() + (16 + 4 * kslots + which) * nbp;
+        return base + g * walker_stride() + (48 + 4 * kc + which) * nbp;
     }
 };
 
-__host__ __device__ inline int group_smem_doubles(int G, int nbp, int kslots)
+__host__ __device__ inline int group_smem_doubles(int G, int nbp, int kc)
 {
-    return G * (16 + 4 * kslots + 2) * nbp;
+    return G * (48 + 4 * kc + 2) * nbp;
 }
 
 // Result of a walker-group evaluation, per thread.
@@ -287,6 +270,85 @@ struct EvalOut {
     double energy;      // local energy of the walker (valid on every thread)
     double lnpsi;       // ln|Psi| of the walker (valid on every thread)
 };
+
+// Accumulators of one thread over its pair tiles.
+struct PairAcc {
+    double T[TB];       // sum_j t_ij of the thread's rows
+    double K;           // sum over the thread's pairs of 1/den^2
+    double pf, pn;      // products of |den| over far / near pairs
+    int ef, en;         // their binary exponents
+    int nnear, npair;
+};
+
+// One 4x4 tile: rows = the thread's particles (tables in registers), columns
+// = block J of the same walker (tables in shared memory).  MASK: the tile is
+// the diagonal block (pairs c1 < c2 only) or touches padding particles.
+template <bool LN, bool EF, bool MASK>
+__device__ __forceinline__ void pair_tile(
+    const DevModel &M, const GroupSmem &sm, int g, int J, int qslot,
+    bool diag, int nvalid, int nvj, const double (&rsa)[TB],
+    const double (&rca)[TB], const double (&rsu)[TB],
+    const double (&rcu)[TB], PairAcc &acc)
+{
+    const int nbp = sm.nbp;
+    const double2 *pa1 = sm.a1(g, 0) + J;
+    const double2 *pa2 = sm.a2(g, 0) + J;
+    const char *pv = reinterpret_cast<const char *>(sm.var(g, 0, 0) + J);
+    const int vstride = 4 * nbp * (int) sizeof(double2);
+#pragma unroll 1
+    for (int c2 = 0; c2 < TB; ++c2) {
+        const double2 A1 = pa1[c2 * nbp];
+        const double2 A2 = pa2[c2 * nbp];
+        const char *pvc = pv + c2 * nbp * (int) sizeof(double2);
+        double fc = 0.0;
+#pragma unroll
+        for (int c1 = 0; c1 < TB; ++c1) {
+            // far branch, in near units: den_f = sin(a_i - a_j) / gamma_f,
+            // num_f = (mu_f / gamma_f) cos(a_i - a_j), mu_f < 0
+            double den_f = fma(rsa[c1], A1.y, -(rca[c1] * A1.x));
+            double num_f = fma(rca[c1], A2.y, rsa[c1] * A2.x);
+            bool near = fabs(den_f) < M.s_m_scaled;
+            // variant of the column tables: bit 1 = unwrapped (cos > 0 <=>
+            // num_f < 0), bit 0 = sigma > 0
+            unsigned hn = (unsigned) __double2hiint(num_f);
+            unsigned hd = (unsigned) __double2hiint(den_f);
+            unsigned v = ((hn >> 31) << 1) | ((hn ^ hd) >> 31);
+            const double2 V = *reinterpret_cast<const double2 *>(
+                pvc + v * vstride);
+            double num_n = fma(rsu[c1], V.y, -(rcu[c1] * V.x));
+            double den_n = fma(rcu[c1], V.y, rsu[c1] * V.x);
+            double num = near ? num_n : num_f;
+            double den = near ? den_n : den_f;
+            double inv = fast_rcp(den);
+            double t = num * inv;
+            if (MASK) {
+                bool ok = (c1 < nvalid) && (c2 < nvj) && (!diag || c1 < c2);
+                t = ok ? t : 0.0;
+                inv = ok ? inv : 0.0;
+                if (LN) {
+                    den_f = ok ? den_f : 1.0;
+                    den_n = ok ? den_n : 1.0;
+                    acc.npair += ok ? 1 : 0;
+                    acc.nnear += (ok && near) ? 1 : 0;
+                }
+            } else if (LN) {
+                acc.npair += 1;
+                acc.nnear += near ? 1 : 0;
+            }
+            if (EF) {
+                acc.T[c1] += t;
+                fc -= t;
+                acc.K = fma(inv, inv, acc.K);
+            }
+            if (LN) {
+                acc.pf *= near ? 1.0 : fabs(den_f);
+                acc.pn *= near ? fabs(den_n) : 1.0;
+            }
+        }
+        if (EF) sm.q(g, qslot, c2)[J] = fc;
+        if (LN) { renorm(acc.pf, acc.ef); renorm(acc.pn, acc.en); }
+    }
+}
 
 // Evaluate drift, local energy (EF) and/or ln|Psi| (LN) of G walkers held by
 // this CTA.  Thread (g, I) owns particles 4I..4I+3 of walker g, positions in
@@ -299,7 +361,7 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
                                            bool active, const double (&z)[TB],
                                            int nvalid, EvalOut &out)
 {
-    const int nb = M.nb, kmax = M.kmax;
+    const int nb = M.nb, kmax = M.kmax, kc = sm.kc;
     double rsa[TB], rca[TB], rsu[TB], rcu[TB];
     double F[TB];
     double e1 = 0.0, ln1 = 0.0;         // one-body partials
@@ -321,88 +383,90 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
                     if (LN) ln1 += ob.lnf;
                 }
             }
-            sm.tab(g, 0, c)[I] = rsa[c];
-            sm.tab(g, 1, c)[I] = rca[c];
-            sm.tab(g, 2, c)[I] = rsu[c];
-            sm.tab(g, 3, c)[I] = rcu[c];
-        }
-    }
-    __syncthreads();
-
-    double kin2 = 0.0;                  // sum over this thread's pairs
-    double pf = 1.0, pn = 1.0;          // ln|f2| products (far / near)
-    int ef = 0, en = 0, nnear = 0;
-    if (active && !M.is_ideal) {
-        const bool even = (nb & 1) == 0;
-        for (int k = 0; k <= kmax; ++k) {
-            // antipodal block column of an even ring: only half the rows
-            if (k > 0 && even && k == kmax && I >= kmax) break;
-            int J = I + k;
-            if (J >= nb) J -= nb;
-            const int nvj = min(TB, M.nop - TB * J);
-            const double *tsa = sm.tab(g, 0, 0) + J;
-            const int nbp = sm.nbp;
-#pragma unroll 1
-            for (int c2 = 0; c2 < TB; ++c2) {
-                double jsa = tsa[(0 * 4 + c2) * nbp];
-                double jca = tsa[(1 * 4 + c2) * nbp];
-                double jsu = tsa[(2 * 4 + c2) * nbp];
-                double jcu = tsa[(3 * 4 + c2) * nbp];
-                double fc = 0.0;
+            if (!M.is_ideal) {
+                sm.a1(g, c)[I] = make_double2(rsa[c] * M.inv_gam,
+                                              rca[c] * M.inv_gam);
+                sm.a2(g, c)[I] = make_double2(rsa[c] * M.mu_over_gam,
+                                              rca[c] * M.mu_over_gam);
 #pragma unroll
-                for (int c1 = 0; c1 < TB; ++c1) {
-                    // diagonal block: c1 < c2 only; padding never counts
-                    bool ok = (c1 < nvalid) && (c2 < nvj)
-                              && (k > 0 || c1 < c2);
-                    double v, kk, ffar, fnear;
-                    int isn;
-                    pair_term<LN>(M, rsa[c1], rca[c1], rsu[c1], rcu[c1],
-                                  jsa, jca, jsu, jcu, v, kk, ffar, fnear,
-                                  isn);
-                    v = ok ? v : 0.0;
-                    kk = ok ? kk : 0.0;
-                    if (EF) {
-                        F[c1] += v;
-                        fc -= v;
-                        kin2 += kk;
-                    }
-                    if (LN) {
-                        pf *= ok ? ffar : 1.0;
-                        pn *= ok ? fnear : 1.0;
-                        nnear += ok ? isn : 0;
-                    }
+                for (int v = 0; v < 4; ++v) {
+                    // v = 2 * unwrapped + (sigma > 0); u_j' = u_j + sigma psi
+                    const int w = (v & 2) ? 0 : 1;
+                    const double cp = M.cpsi[w];
+                    const double sp = (v & 1) ? M.spsi[w] : -M.spsi[w];
+                    sm.var(g, v, c)[I] = make_double2(
+                        fma(rsu[c], cp, rcu[c] * sp),
+                        fma(rcu[c], cp, -(rsu[c] * sp)));
                 }
-                if (EF) sm.q(g, k, c2)[J] = fc;
-                if (LN) { renorm(pf, ef); renorm(pn, en); }
             }
         }
     }
     __syncthreads();
 
-    double epart = 0.0, lpart = 0.0;
-    if (active) {
-        if (EF && !M.is_ideal) {
-            const bool even = (nb & 1) == 0;
-            for (int k = 0; k <= kmax; ++k) {
-                // slot k, column I was written by row block I - k
-                if (k > 0 && even && k == kmax && I < kmax) continue;
+    PairAcc acc;
 #pragma unroll
-                for (int c = 0; c < TB; ++c) F[c] += sm.q(g, k, c)[I];
+    for (int c = 0; c < TB; ++c) acc.T[c] = 0.0;
+    acc.K = 0.0; acc.pf = 1.0; acc.pn = 1.0;
+    acc.ef = 0; acc.en = 0; acc.nnear = 0; acc.npair = 0;
+    double Tq[TB] = {0., 0., 0., 0.};   // column sums received from others
+    const bool pairs = active && !M.is_ideal;
+    const bool even = (nb & 1) == 0;
+    for (int k0 = 0; k0 <= kmax; k0 += kc) {
+        const int k1 = min(k0 + kc, kmax + 1);
+        if (pairs) {
+            for (int k = k0; k < k1; ++k) {
+                // antipodal block column of an even ring: half the rows
+                if (k > 0 && even && k == kmax && I >= kmax) break;
+                int J = I + k;
+                if (J >= nb) J -= nb;
+                const int nvj = min(TB, M.nop - TB * J);
+                if (LN || k == 0 || nvalid < TB || nvj < TB)
+                    pair_tile<LN, EF, true>(M, sm, g, J, k - k0, k == 0,
+                                            nvalid, nvj, rsa, rca, rsu, rcu,
+                                            acc);
+                else
+                    pair_tile<LN, EF, false>(M, sm, g, J, k - k0, false,
+                                             nvalid, nvj, rsa, rca, rsu, rcu,
+                                             acc);
             }
         }
         if (EF) {
+            __syncthreads();
+            if (pairs) {
+                for (int k = k0; k < k1; ++k) {
+                    // slot k, column I was written by row block I - k
+                    if (k > 0 && even && k == kmax && I < kmax) continue;
+#pragma unroll
+                    for (int c = 0; c < TB; ++c)
+                        Tq[c] += sm.q(g, k - k0, c)[I];
+                }
+            }
+            if (k1 <= kmax) __syncthreads();
+        }
+    }
+    if (!EF) __syncthreads();
+
+    double epart = 0.0, lpart = 0.0;
+    if (active) {
+        if (EF) {
             double f2 = 0.0;
 #pragma unroll
-            for (int c = 0; c < TB; ++c)
+            for (int c = 0; c < TB; ++c) {
+                F[c] = fma(M.drift_unit, acc.T[c] + Tq[c], F[c]);
                 if (c < nvalid) f2 = fma(F[c], F[c], f2);
-            epart = e1 + 2.0 * kin2 - f2;
+            }
+            epart = e1 + 2.0 * M.kin_unit * acc.K - f2;
             sm.red(g, 0)[I] = epart;
         }
         if (LN) {
             lpart = ln1;
-            if (!M.is_ideal)
-                lpart += M.beta * (log(pf) + ef * LN2)
-                         + (log(pn) + en * LN2) + nnear * M.ln_am;
+            if (!M.is_ideal) {
+                const int nfar = acc.npair - acc.nnear;
+                lpart += M.beta * (log(acc.pf) + acc.ef * LN2
+                                   + nfar * M.ln_gam)
+                         + (log(acc.pn) + acc.en * LN2)
+                         + acc.nnear * M.ln_am;
+            }
             sm.red(g, 1)[I] = lpart;
         }
     }

@@ -22,13 +22,13 @@ __device__ __forceinline__ GroupIdx group_index(const DevModel &M, int G)
     return x;
 }
 
-__device__ __forceinline__ GroupSmem group_smem(const DevModel &M, int nbp)
+__device__ __forceinline__ GroupSmem group_smem(const GroupGeom &geom)
 {
-    extern __shared__ double qmcb_smem[];
+    extern __shared__ __align__(16) double qmcb_smem[];
     GroupSmem sm;
     sm.base = qmcb_smem;
-    sm.nbp = nbp;
-    sm.kslots = M.kmax + 1;
+    sm.nbp = geom.nbp;
+    sm.kc = geom.kc;
     return sm;
 }
 
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256)
 model_eval_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                   EvalArgs a)
 {
-    GroupSmem sm = group_smem(M, geom.nbp);
+    GroupSmem sm = group_smem(geom);
     GroupIdx x = group_index(M, geom.G);
     const int N = M.nop;
     const bool vec_ok = (N % 2) == 0;
@@ -370,7 +370,7 @@ dmc_step_kernel(const __grid_constant__ DevModel M, GroupGeom geom, DmcBufs B,
     double *nenergy = B.energy[par ^ 1];
     double *nweight = B.weight[par ^ 1];
 
-    GroupSmem sm = group_smem(M, geom.nbp);
+    GroupSmem sm = group_smem(geom);
     GroupIdx x = group_index(M, geom.G);
     const int N = M.nop;
     const bool vec_ok = (N % 2) == 0;
