@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libqmcb200.so')
+# QMCB_LIB selects a tuning variant built by scripts/ (development aid)
+LIB_PATH = os.environ.get('QMCB_LIB') or os.path.join(_HERE, 'libqmcb200.so')
 
 # Every symbol include/qmcb200.h declares (tests check the export table).
 SYMBOLS = [

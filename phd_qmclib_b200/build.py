@@ -9,6 +9,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libqmcb200.so')
 SOURCES = ['qmcb_api.cu']
 DEPS = ['qmcb_api.cu', 'qmcb_kernels.cuh', 'qmcb_dev.cuh',
+        'qmcb_estimators.cuh',
         os.path.join('..', '..', 'include', 'qmcb200.h')]
 
 NVCC_FLAGS = [
@@ -26,11 +27,14 @@ def needs_build():
                if os.path.exists(os.path.join(CSRC, d)))
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """``defines`` / ``out``: build a tuning variant next to the product
+    library (development aid, see scripts/)."""
+    lib = out or LIB
+    if not force and not defines and not needs_build():
         return LIB
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB] + \
+    cmd = [nvcc] + NVCC_FLAGS + ['-D' + d for d in defines] + ['-o', lib] + \
         [os.path.join(CSRC, s) for s in SOURCES] + ['-ldl']
     env = dict(os.environ)
     # the image's $CC wrapper is not a usable host compiler for nvcc
@@ -41,9 +45,10 @@ def build(force=False, verbose=False):
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed building libqmcb200.so')
-    with open(os.path.join(HERE, 'build.log'), 'w') as f:
-        f.write(' '.join(cmd) + '\n' + res.stdout + res.stderr)
-    return LIB
+    if not out:
+        with open(os.path.join(HERE, 'build.log'), 'w') as f:
+            f.write(' '.join(cmd) + '\n' + res.stdout + res.stderr)
+    return lib
 
 
 if __name__ == '__main__':

@@ -13,10 +13,13 @@
 
 #include "../../include/qmcb200.h"
 #include "qmcb_kernels.cuh"
+#include "qmcb_estimators.cuh"
 
 using namespace qmcb;
 
 namespace {
+
+constexpr int CS_BLOCKS = 296;      // CTAs of the column-sum kernels (2 / SM)
 
 std::string g_create_error;
 
@@ -106,6 +109,16 @@ struct qmcb_handle {
     double last_total_ms = 0.0, last_step_ms = 0.0;
     long long last_launches = 0;
 
+    // estimators (device)
+    double *ssf_aux[2] = {nullptr, nullptr};    // [cap][M][3] ping-pong
+    double *ssf_iter = nullptr;                 // [log_cap][M][3]
+    double *den_hist[2] = {nullptr, nullptr};   // [cap][B] (2nd: mixed only)
+    double *den_total = nullptr;                // [2][B]
+    double *den_iter = nullptr;                 // [log_cap][B]
+    double *est_partial = nullptr;              // [CS_BLOCKS][max(3M, B)]
+    int *den_hi = nullptr;                      // highest slot count seen
+    long long est_log_cap = 0;
+
     // multi-GPU
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
@@ -192,8 +205,10 @@ bool build_model(const qmcb_model_params &p, DevModel &M, std::string &err)
     M.mu_over_gam = M.is_ideal ? 0.0 : -(M_PI / M.L) * beta / (k2 * gam);
     M.s_m_scaled = s_m / gam;
     M.ln_gam = std::log(gam);
-    M.drift_unit = -k2;
-    M.kin_unit = k2 * k2;
+    M.drift_unit = M.is_ideal ? 1.0 : -k2;
+    M.kin_unit = M.is_ideal ? 1.0 : k2 * k2;
+    M.inv_drift_unit = 1.0 / M.drift_unit;
+    M.half_inv_kin_unit = 0.5 / M.kin_unit;
     double psi0 = k2 * r_off, psi1 = k2 * r_off - k2 * M.L;
     M.cpsi[0] = std::cos(psi0); M.spsi[0] = std::sin(psi0);
     M.cpsi[1] = std::cos(psi1); M.spsi[1] = std::sin(psi1);
@@ -227,7 +242,7 @@ bool choose_geom(const DevModel &M, int max_smem, GroupGeom &g,
             for (int kc = kfull; kc >= 1; kc = (kc > 4 ? (kc + 1) / 2 : kc - 1))
                 kcs.push_back(kc);
         for (int kc : kcs) {
-            int bytes = group_smem_doubles(G, nbp, kc) * 8;
+            int bytes = group_smem_doubles(G, nbp, M.nb, kc) * 8;
             if (bytes > max_smem) continue;
             int by_smem = (228 * 1024) / (bytes + 1024);
             int ctas = std::min(by_smem, std::min(by_regs, by_thr));
@@ -239,6 +254,8 @@ bool choose_geom(const DevModel &M, int max_smem, GroupGeom &g,
             if (score > best + 1e-9) {
                 best = score;
                 g.nthreads = nt; g.G = G; g.nbp = nbp; g.kc = kc;
+                g.tab_stride = group_tab_stride(nbp, M.nb);
+                g.q_stride = group_q_stride(nbp, M.nb, kc);
                 g.smem_bytes = bytes;
             }
         }
@@ -301,6 +318,15 @@ void free_dmc(qmcb_handle *h)
     cudaFree(B.slot_energy); cudaFree(B.ref); cudaFree(B.cnt);
     cudaFree(B.blocksum); cudaFree(B.blockoff); cudaFree(B.epart);
     cudaFree(B.ctl);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(h->ssf_aux[i]); cudaFree(h->den_hist[i]);
+        h->ssf_aux[i] = nullptr; h->den_hist[i] = nullptr;
+    }
+    cudaFree(h->ssf_iter); cudaFree(h->den_total); cudaFree(h->den_iter);
+    cudaFree(h->est_partial); cudaFree(h->den_hi);
+    h->ssf_iter = h->den_total = h->den_iter = h->est_partial = nullptr;
+    h->den_hi = nullptr;
+    h->est_log_cap = 0;
     cudaFree(h->L.energy); cudaFree(h->L.weight); cudaFree(h->L.ref_energy);
     cudaFree(h->L.accum_energy); cudaFree(h->L.num_walkers);
     B = DmcBufs{};
@@ -324,7 +350,13 @@ int alloc_dmc(qmcb_handle *h, const qmcb_dmc_params *p,
     const int N = h->M.nop;
     size_t cb = (size_t) cap * 2 * N * sizeof(double);
     // a restart with the same capacity keeps the device allocation
-    const bool reuse = B.confs[0] != nullptr && B.cap == (int) cap;
+    if (p->ssf_num_modes < 0 || p->density_num_bins < 0
+        || p->ssf_num_modes > 65536 || p->density_num_bins > (1 << 24))
+        FAIL(h, QMCB_ERR_INVALID, "bad estimator sizes");
+    const bool reuse = B.confs[0] != nullptr && B.cap == (int) cap
+                       && h->dp.ssf_num_modes == p->ssf_num_modes
+                       && h->dp.density_num_bins == p->density_num_bins
+                       && h->dp.density_as_pure == p->density_as_pure;
     if (!reuse) {
         free_dmc(h);
         B.cap = (int) cap;
@@ -343,6 +375,24 @@ int alloc_dmc(qmcb_handle *h, const qmcb_dmc_params *p,
         CUDA_TRY(h, cudaMalloc(&B.ctl, sizeof(DmcCtl)));
         for (int i = 0; i < 2; ++i)
             CUDA_TRY(h, cudaMemsetAsync(B.confs[i], 0, cb, h->stream));
+        const size_t M3 = (size_t) p->ssf_num_modes * 3;
+        const size_t NB = (size_t) p->density_num_bins;
+        if (M3)
+            for (int i = 0; i < 2; ++i)
+                CUDA_TRY(h, cudaMalloc(&h->ssf_aux[i],
+                                       cap * M3 * sizeof(double)));
+        if (NB) {
+            const int nh = p->density_as_pure ? 1 : 2;
+            for (int i = 0; i < nh; ++i)
+                CUDA_TRY(h, cudaMalloc(&h->den_hist[i],
+                                       cap * NB * sizeof(double)));
+            CUDA_TRY(h, cudaMalloc(&h->den_total, 2 * NB * sizeof(double)));
+            CUDA_TRY(h, cudaMalloc(&h->den_hi, sizeof(int)));
+        }
+        if (M3 || NB)
+            CUDA_TRY(h, cudaMalloc(&h->est_partial,
+                                   CS_BLOCKS * std::max(M3, NB)
+                                       * sizeof(double)));
     }
     h->dmc_ready = false;
     h->dp = *p;
@@ -367,6 +417,96 @@ int alloc_dmc(qmcb_handle *h, const qmcb_dmc_params *p,
     C.seed = p->rng_seed;
     C.slot_offset = slot_offset;
     C.energy_mode = p->energy_mode;
+    return QMCB_OK;
+}
+
+int ensure_est_log(qmcb_handle *h, long long nts)
+{
+    if (nts <= h->est_log_cap) return QMCB_OK;
+    cudaFree(h->ssf_iter); cudaFree(h->den_iter);
+    h->ssf_iter = h->den_iter = nullptr;
+    h->est_log_cap = 0;
+    const size_t M3 = (size_t) h->dp.ssf_num_modes * 3;
+    const size_t NB = (size_t) h->dp.density_num_bins;
+    if (M3) CUDA_TRY(h, cudaMalloc(&h->ssf_iter, nts * M3 * sizeof(double)));
+    if (NB) CUDA_TRY(h, cudaMalloc(&h->den_iter, nts * NB * sizeof(double)));
+    h->est_log_cap = nts;
+    return QMCB_OK;
+}
+
+// One step of the S(k) estimator on the "actual" population
+// (qmc_base/jastrow/dmc.py:363-573): step_idx counts from the block start.
+int launch_ssf_step(qmcb_handle *h, long long step_idx)
+{
+    DmcBufs &B = h->B;
+    const int M = h->dp.ssf_num_modes, N = h->M.nop;
+    const bool pure = h->dp.ssf_as_pure != 0;
+    const long long pfw = h->dp.ssf_pfw_nts;
+    const int cur = (int) (step_idx & 1);
+    int *W_dev = (int *) ((char *) B.ctl + offsetof(DmcCtl, W));
+    double *out = h->ssf_aux[cur];
+    const double *prev = h->ssf_aux[cur ^ 1];
+    if (pure && step_idx >= pfw) {
+        rows_gather_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(
+            prev, B.ref, W_dev, 3 * M, out);
+    } else {
+        SsfArgs a{};
+        // parent buffer of the step in flight: parity of ctl->step, which
+        // the host mirrors in step_host
+        a.confs = B.confs[(int) ((h->step_host + step_idx) & 1)];
+        a.ref = B.ref; a.W_dev = W_dev; a.N = N; a.M = M;
+        a.two_over_L = 2.0 / h->M.L;
+        a.out = out; a.prev = prev; a.accumulate = pure ? 1 : 0;
+        int nchunk = (M + SSF_CHUNK - 1) / SSF_CHUNK;
+        int G = std::max(1, SSF_THREADS / nchunk);
+        G = std::min(G, std::max(1, (40 * 1024) / (24 * N)));
+        size_t smem = (size_t) 3 * G * N * sizeof(double);
+        int grid = std::min((B.cap + G - 1) / G, h->sm_count * 16);
+        ssf_eval_kernel<<<grid, SSF_THREADS, smem, h->stream>>>(a, G, nchunk);
+    }
+    RowRange rr{};
+    rr.hi_dev = W_dev; rr.lo_host = 0;
+    colsum_partial_kernel<<<CS_BLOCKS, 256, 0, h->stream>>>(
+        out, rr, 3 * M, h->est_partial);
+    double div = 1.0;
+    if (pure) div = (double) std::min(step_idx + 1, pfw);
+    colsum_final_kernel<<<(3 * M + 127) / 128, 128, 0, h->stream>>>(
+        h->est_partial, CS_BLOCKS, 3 * M, nullptr, 1.0, 1.0 / div,
+        h->ssf_iter + step_idx * 3 * M);
+    CUDA_TRY(h, cudaGetLastError());
+    return QMCB_OK;
+}
+
+// One step of the density estimator (mrbp_qmc/dmc.py:472-547).  Pure mode
+// ignores the genealogy (quirk Q2), so the reference's ping-pong copy of all
+// slots is the same as one in-place per-slot histogram; mixed mode keeps the
+// two parity buffers the reference accumulates into (quirk Q3).
+int launch_density_step(qmcb_handle *h, long long step_idx)
+{
+    DmcBufs &B = h->B;
+    const int NB = h->dp.density_num_bins, N = h->M.nop;
+    const bool pure = h->dp.density_as_pure != 0;
+    const long long pfw = h->dp.density_pfw_nts;
+    const int pbuf = pure ? 0 : (int) (step_idx & 1);
+    int *W_dev = (int *) ((char *) B.ctl + offsetof(DmcCtl, W));
+    double *hist = h->den_hist[pbuf];
+    double *total = h->den_total + (size_t) pbuf * NB;
+    if (!pure || step_idx < pfw) {
+        const double *confs = B.confs[(int) ((h->step_host + step_idx) & 1)];
+        density_hist_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(
+            confs, B.ref, W_dev, N, NB, h->M.L / NB, hist, total, h->den_hi);
+    }
+    // sum over live slots = running total - rows of slots that died
+    RowRange rr{};
+    rr.lo_dev = W_dev; rr.hi_dev = h->den_hi;
+    colsum_partial_kernel<<<CS_BLOCKS, 256, 0, h->stream>>>(
+        hist, rr, NB, h->est_partial);
+    double div = 1.0;
+    if (pure) div = (double) std::min(step_idx + 1, pfw);
+    colsum_final_kernel<<<(NB + 127) / 128, 128, 0, h->stream>>>(
+        h->est_partial, CS_BLOCKS, NB, total, -1.0, 1.0 / div,
+        h->den_iter + step_idx * NB);
+    CUDA_TRY(h, cudaGetLastError());
     return QMCB_OK;
 }
 
@@ -547,11 +687,37 @@ int qmcb_model_eval(qmcb_handle *h, const double *confs, int64_t nconf,
     return QMCB_OK;
 }
 
-int qmcb_fourier_density(qmcb_handle *h, const double *, int64_t, int32_t,
-                         double *)
+int qmcb_fourier_density(qmcb_handle *h, const double *confs, int64_t nconf,
+                         int32_t num_modes, double *out)
 {
     if (!h) return QMCB_ERR_INVALID;
-    FAIL(h, QMCB_ERR_STATE, "qmcb_fourier_density: not implemented yet");
+    if (nconf < 0 || num_modes < 1 || (nconf > 0 && (!confs || !out)))
+        FAIL(h, QMCB_ERR_INVALID, "bad arguments");
+    if (nconf == 0) return QMCB_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int N = h->M.nop, M = num_modes;
+    size_t nc = (size_t) nconf * 2 * N, no = (size_t) nconf * M * 3;
+    int rc = ensure_scratch(h, (nc + no) * sizeof(double));
+    if (rc) return rc;
+    double *d_confs = h->d_scratch, *d_out = d_confs + nc;
+    CUDA_TRY(h, cudaMemcpyAsync(d_confs, confs, nc * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+    SsfArgs a{};
+    a.confs = d_confs; a.W_host = nconf; a.N = N; a.M = M;
+    a.two_over_L = 2.0 / h->M.L;
+    a.out = d_out;
+    int nchunk = (M + SSF_CHUNK - 1) / SSF_CHUNK;
+    int G = std::max(1, SSF_THREADS / nchunk);
+    G = std::min(G, std::max(1, (40 * 1024) / (24 * N)));
+    size_t smem = (size_t) 3 * G * N * sizeof(double);
+    int grid = (int) std::min<long long>((nconf + G - 1) / G,
+                                         h->sm_count * 16);
+    ssf_eval_kernel<<<grid, SSF_THREADS, smem, h->stream>>>(a, G, nchunk);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemcpyAsync(out, d_out, no * sizeof(double),
+                                cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return QMCB_OK;
 }
 
 int qmcb_dmc_init(qmcb_handle *h, const qmcb_dmc_params *params,
@@ -670,10 +836,37 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
     if (!h) return QMCB_ERR_INVALID;
     if (!h->dmc_ready) FAIL(h, QMCB_ERR_STATE, "qmcb_dmc_init not called");
     if (nts < 1) FAIL(h, QMCB_ERR_INVALID, "nts must be >= 1");
-    (void) eval_estimators; (void) density; (void) ssf;
     CUDA_TRY(h, cudaSetDevice(h->device));
     int rc = ensure_log(h, nts);
     if (rc) return rc;
+    const int M3 = 3 * h->dp.ssf_num_modes, NB = h->dp.density_num_bins;
+    const bool do_ssf = eval_estimators && M3 > 0;
+    const bool do_den = eval_estimators && NB > 0;
+    const size_t cap_sz = (size_t) h->B.cap;
+    if (do_ssf || do_den) {
+        // qmc_base/dmc.py:901-909: every block starts from zeroed tables
+        rc = ensure_est_log(h, nts);
+        if (rc) return rc;
+        if (do_ssf) {
+            for (int i = 0; i < 2; ++i)
+                CUDA_TRY(h, cudaMemsetAsync(h->ssf_aux[i], 0,
+                                            cap_sz * M3 * sizeof(double),
+                                            h->stream));
+        }
+        if (do_den) {
+            for (int i = 0; i < 2; ++i)
+                if (h->den_hist[i])
+                    CUDA_TRY(h, cudaMemsetAsync(h->den_hist[i], 0,
+                                                cap_sz * NB * sizeof(double),
+                                                h->stream));
+            CUDA_TRY(h, cudaMemsetAsync(h->den_total, 0,
+                                        2 * (size_t) NB * sizeof(double),
+                                        h->stream));
+            CUDA_TRY(h, cudaMemsetAsync(h->den_hi, 0, sizeof(int),
+                                        h->stream));
+        }
+    }
+    long long est_launches = 0;
     DmcBufs &B = h->B;
     DmcLog L = h->L;
     L.block_step0 = h->step_host;
@@ -706,12 +899,30 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
             h->M, g, B, h->C);
         if (h->profile_steps)
             CUDA_TRY(h, cudaEventRecord(h->step_ev[2 * i + 1], h->stream));
+        if (do_den) {
+            rc = launch_density_step(h, i);
+            if (rc) return rc;
+            est_launches += 3;
+        }
+        if (do_ssf) {
+            rc = launch_ssf_step(h, i);
+            if (rc) return rc;
+            est_launches += 3;
+        }
         dmc_finalize_kernel<<<1, 32, 0, h->stream>>>(B, h->C, L);
     }
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     h->step_host += nts;
-    h->last_launches = (6 + (h->comm ? 1 : 0)) * nts;
+    h->last_launches = (6 + (h->comm ? 1 : 0)) * nts + est_launches;
+    if (density && do_den)
+        CUDA_TRY(h, cudaMemcpyAsync(density, h->den_iter,
+                                    nts * (size_t) NB * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (ssf && do_ssf)
+        CUDA_TRY(h, cudaMemcpyAsync(ssf, h->ssf_iter,
+                                    nts * (size_t) M3 * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
     if (energy)
         CUDA_TRY(h, cudaMemcpyAsync(energy, L.energy, nts * sizeof(double),
                                     cudaMemcpyDeviceToHost, h->stream));

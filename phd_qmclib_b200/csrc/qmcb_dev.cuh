@@ -55,8 +55,9 @@ struct DevModel {
     double s_m_scaled;                // sin(pi r_m / L) / gamma_f
     double ln_gam;                    // ln gamma_f
     double cpsi[2], spsi[2];          // cos/sin(psi_w)
-    double drift_unit;                // -k2
-    double kin_unit;                  // k2^2
+    double drift_unit;                // -k2       (1 if is_ideal)
+    double kin_unit;                  // k2^2      (1 if is_ideal)
+    double inv_drift_unit, half_inv_kin_unit;
 };
 
 // Launch geometry shared by every walker-group kernel.
@@ -65,8 +66,23 @@ struct GroupGeom {
     int G;              // walkers per CTA
     int nbp;            // padded row length of the shared tables (>= nb, even)
     int kc;             // column-sum slots kept in shared memory at a time
+    int tab_stride;     // doubles between the table regions of two walkers
+    int q_stride;       // doubles between their column-sum regions
     int smem_bytes;
 };
+
+// Lane t = nb g + I of a CTA reads element J of walker g.  With the walker
+// regions spaced so that (stride mod 128 B) equals (nb elements mod 128 B),
+// the lanes of two neighbouring walkers continue each other's bank sequence
+// and a warp that straddles walkers loads without bank conflicts.
+__host__ __device__ inline int bank_aligned_stride(int min_doubles, int nb,
+                                                   int elem_doubles)
+{
+    int want = (nb * elem_doubles) % 16;
+    int s = min_doubles;
+    while (s % 16 != want) ++s;
+    return s;
+}
 
 // ---------------------------------------------------------------------------
 // small helpers
@@ -83,8 +99,12 @@ __device__ __forceinline__ double fast_rcp(double x)
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-x, y, 1.0);
+#ifdef QMCB_RCP_NEWTON2
+    return fma(y, e, y);
+#else
     double p = fma(e, e, e);
     return fma(y, p, y);
+#endif
 }
 
 // Pull the binary exponent of p (> 0) into e, leaving p in [1, 2).
@@ -229,39 +249,52 @@ __device__ __forceinline__ void particle_tables(const DevModel &M, double z,
 // ---------------------------------------------------------------------------
 struct GroupSmem {
     double *base;
-    int nbp, kc;
-    __device__ __forceinline__ int walker_stride() const
+    int nbp, kc, G, tab_stride, q_stride;
+    __device__ __forceinline__ double *tab(int g) const
     {
-        return (48 + 4 * kc + 2) * nbp;
+        return base + g * tab_stride;
+    }
+    __device__ __forceinline__ double *qreg(int g) const
+    {
+        return base + G * tab_stride + g * q_stride;
     }
     __device__ __forceinline__ double2 *a1(int g, int c) const
     {
-        return reinterpret_cast<double2 *>(base + g * walker_stride())
-               + c * nbp;
+        return reinterpret_cast<double2 *>(tab(g)) + c * nbp;
     }
     __device__ __forceinline__ double2 *a2(int g, int c) const
     {
-        return reinterpret_cast<double2 *>(base + g * walker_stride()
-                                           + 8 * nbp) + c * nbp;
+        return reinterpret_cast<double2 *>(tab(g) + 8 * nbp) + c * nbp;
     }
     __device__ __forceinline__ double2 *var(int g, int v, int c) const
     {
-        return reinterpret_cast<double2 *>(base + g * walker_stride()
-                                           + 16 * nbp) + (v * 4 + c) * nbp;
+        return reinterpret_cast<double2 *>(tab(g) + 16 * nbp)
+               + (v * 4 + c) * nbp;
     }
     __device__ __forceinline__ double *q(int g, int k, int c) const
     {
-        return base + g * walker_stride() + (48 + k * 4 + c) * nbp;
+        return qreg(g) + (k * 4 + c) * nbp;
     }
     __device__ __forceinline__ double *red(int g, int which) const
     {
-        return base + g * walker_stride() + (48 + 4 * kc + which) * nbp;
+        return qreg(g) + (4 * kc + which) * nbp;
     }
 };
 
-__host__ __device__ inline int group_smem_doubles(int G, int nbp, int kc)
+__host__ __device__ inline int group_tab_stride(int nbp, int nb)
 {
-    return G * (48 + 4 * kc + 2) * nbp;
+    return bank_aligned_stride(48 * nbp, nb, 2);
+}
+
+__host__ __device__ inline int group_q_stride(int nbp, int nb, int kc)
+{
+    return bank_aligned_stride((4 * kc + 2) * nbp, nb, 1);
+}
+
+__host__ __device__ inline int group_smem_doubles(int G, int nbp, int nb,
+                                                  int kc)
+{
+    return G * (group_tab_stride(nbp, nb) + group_q_stride(nbp, nb, kc));
 }
 
 // Result of a walker-group evaluation, per thread.
@@ -291,34 +324,52 @@ __device__ __forceinline__ void pair_tile(
     const double (&rcu)[TB], PairAcc &acc)
 {
     const int nbp = sm.nbp;
-    const double2 *pa1 = sm.a1(g, 0) + J;
-    const double2 *pa2 = sm.a2(g, 0) + J;
+    const int cstride = nbp * (int) sizeof(double2);    // next column particle
+    const unsigned vstride = 4u * (unsigned) cstride;   // next variant
+    const char *pa1 = reinterpret_cast<const char *>(sm.a1(g, 0) + J);
+    const char *pa2 = reinterpret_cast<const char *>(sm.a2(g, 0) + J);
     const char *pv = reinterpret_cast<const char *>(sm.var(g, 0, 0) + J);
-    const int vstride = 4 * nbp * (int) sizeof(double2);
+    double *pq = sm.q(g, qslot, 0) + J;
+    const double s_m = M.s_m_scaled;
+    double2 A1 = *reinterpret_cast<const double2 *>(pa1);
+    double2 A2 = *reinterpret_cast<const double2 *>(pa2);
 #pragma unroll 1
     for (int c2 = 0; c2 < TB; ++c2) {
-        const double2 A1 = pa1[c2 * nbp];
-        const double2 A2 = pa2[c2 * nbp];
-        const char *pvc = pv + c2 * nbp * (int) sizeof(double2);
+        // phase 1: far branch in near units for the four rows,
+        //   den_f = sin(a_i - a_j) / gamma_f,
+        //   num_f = (mu_f / gamma_f) cos(a_i - a_j),  mu_f < 0,
+        // and the column-table variant each pair needs: bit 1 = unwrapped
+        // (cos > 0 <=> num_f < 0), bit 0 = sigma > 0
+        double den_f[TB], num_f[TB];
+        double2 V[TB];
+#pragma unroll
+        for (int c1 = 0; c1 < TB; ++c1) {
+            den_f[c1] = fma(rsa[c1], A1.y, -(rca[c1] * A1.x));
+            num_f[c1] = fma(rca[c1], A2.y, rsa[c1] * A2.x);
+        }
+#pragma unroll
+        for (int c1 = 0; c1 < TB; ++c1) {
+            unsigned hn = (unsigned) __double2hiint(num_f[c1]);
+            unsigned hd = (unsigned) __double2hiint(den_f[c1]);
+            unsigned v = ((hn >> 31) << 1) + ((hn ^ hd) >> 31);
+            V[c1] = *reinterpret_cast<const double2 *>(pv + v * vstride);
+        }
+        // next column particle's far tables, in flight during phase 2
+        if (c2 + 1 < TB) {
+            pa1 += cstride; pa2 += cstride;
+            A1 = *reinterpret_cast<const double2 *>(pa1);
+            A2 = *reinterpret_cast<const double2 *>(pa2);
+        }
+        pv += cstride;
+        // phase 2: near branch, select, one reciprocal per pair
         double fc = 0.0;
 #pragma unroll
         for (int c1 = 0; c1 < TB; ++c1) {
-            // far branch, in near units: den_f = sin(a_i - a_j) / gamma_f,
-            // num_f = (mu_f / gamma_f) cos(a_i - a_j), mu_f < 0
-            double den_f = fma(rsa[c1], A1.y, -(rca[c1] * A1.x));
-            double num_f = fma(rca[c1], A2.y, rsa[c1] * A2.x);
-            bool near = fabs(den_f) < M.s_m_scaled;
-            // variant of the column tables: bit 1 = unwrapped (cos > 0 <=>
-            // num_f < 0), bit 0 = sigma > 0
-            unsigned hn = (unsigned) __double2hiint(num_f);
-            unsigned hd = (unsigned) __double2hiint(den_f);
-            unsigned v = ((hn >> 31) << 1) | ((hn ^ hd) >> 31);
-            const double2 V = *reinterpret_cast<const double2 *>(
-                pvc + v * vstride);
-            double num_n = fma(rsu[c1], V.y, -(rcu[c1] * V.x));
-            double den_n = fma(rcu[c1], V.y, rsu[c1] * V.x);
-            double num = near ? num_n : num_f;
-            double den = near ? den_n : den_f;
+            bool near = fabs(den_f[c1]) < s_m;
+            double num_n = fma(rsu[c1], V[c1].y, -(rcu[c1] * V[c1].x));
+            double den_n = fma(rcu[c1], V[c1].y, rsu[c1] * V[c1].x);
+            double num = near ? num_n : num_f[c1];
+            double den = near ? den_n : den_f[c1];
             double inv = fast_rcp(den);
             double t = num * inv;
             if (MASK) {
@@ -326,7 +377,7 @@ __device__ __forceinline__ void pair_tile(
                 t = ok ? t : 0.0;
                 inv = ok ? inv : 0.0;
                 if (LN) {
-                    den_f = ok ? den_f : 1.0;
+                    den_f[c1] = ok ? den_f[c1] : 1.0;
                     den_n = ok ? den_n : 1.0;
                     acc.npair += ok ? 1 : 0;
                     acc.nnear += (ok && near) ? 1 : 0;
@@ -341,11 +392,11 @@ __device__ __forceinline__ void pair_tile(
                 acc.K = fma(inv, inv, acc.K);
             }
             if (LN) {
-                acc.pf *= near ? 1.0 : fabs(den_f);
+                acc.pf *= near ? 1.0 : fabs(den_f[c1]);
                 acc.pn *= near ? fabs(den_n) : 1.0;
             }
         }
-        if (EF) sm.q(g, qslot, c2)[J] = fc;
+        if (EF) { *pq = fc; pq += nbp; }
         if (LN) { renorm(acc.pf, acc.ef); renorm(acc.pn, acc.en); }
     }
 }
@@ -363,14 +414,19 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
 {
     const int nb = M.nb, kmax = M.kmax, kc = sm.kc;
     double rsa[TB], rca[TB], rsu[TB], rcu[TB];
-    double F[TB];
-    double e1 = 0.0, ln1 = 0.0;         // one-body partials
+    PairAcc acc;
+    // The one-body terms ride in the pair accumulators (in their units):
+    // T starts at f1'/f1 / drift_unit, K at (kin1 + V) / (2 kin_unit).
+    acc.K = 0.0; acc.pf = 1.0; acc.pn = 1.0;
+    acc.ef = 0; acc.en = 0; acc.nnear = 0; acc.npair = 0;
+    double ln1 = 0.0;
 #pragma unroll
     for (int c = 0; c < TB; ++c) {
-        F[c] = 0.0;
+        acc.T[c] = 0.0;
         rsa[c] = 0.0; rca[c] = 1.0; rsu[c] = 0.0; rcu[c] = 1.0;
     }
     if (active) {
+        double e1 = 0.0;
 #pragma unroll
         for (int c = 0; c < TB; ++c) {
             if (c < nvalid) {
@@ -378,7 +434,7 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
                     particle_tables(M, z[c], rsa[c], rca[c], rsu[c], rcu[c]);
                 if (!M.is_free) {
                     OneBody ob = one_body<LN>(M, z[c]);
-                    F[c] = ob.ldz;
+                    acc.T[c] = ob.ldz * M.inv_drift_unit;
                     e1 += ob.kin + ob.pot;
                     if (LN) ln1 += ob.lnf;
                 }
@@ -400,14 +456,10 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
                 }
             }
         }
+        acc.K = e1 * M.half_inv_kin_unit;
     }
     __syncthreads();
 
-    PairAcc acc;
-#pragma unroll
-    for (int c = 0; c < TB; ++c) acc.T[c] = 0.0;
-    acc.K = 0.0; acc.pf = 1.0; acc.pn = 1.0;
-    acc.ef = 0; acc.en = 0; acc.nnear = 0; acc.npair = 0;
     double Tq[TB] = {0., 0., 0., 0.};   // column sums received from others
     const bool pairs = active && !M.is_ideal;
     const bool even = (nb & 1) == 0;
@@ -447,15 +499,16 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
     if (!EF) __syncthreads();
 
     double epart = 0.0, lpart = 0.0;
+    double F[TB] = {0., 0., 0., 0.};
     if (active) {
         if (EF) {
             double f2 = 0.0;
 #pragma unroll
             for (int c = 0; c < TB; ++c) {
-                F[c] = fma(M.drift_unit, acc.T[c] + Tq[c], F[c]);
+                F[c] = M.drift_unit * (acc.T[c] + Tq[c]);
                 if (c < nvalid) f2 = fma(F[c], F[c], f2);
             }
-            epart = e1 + 2.0 * M.kin_unit * acc.K - f2;
+            epart = 2.0 * M.kin_unit * acc.K - f2;
             sm.red(g, 0)[I] = epart;
         }
         if (LN) {

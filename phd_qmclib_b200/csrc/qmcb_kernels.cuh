@@ -29,6 +29,9 @@ __device__ __forceinline__ GroupSmem group_smem(const GroupGeom &geom)
     sm.base = qmcb_smem;
     sm.nbp = geom.nbp;
     sm.kc = geom.kc;
+    sm.G = geom.G;
+    sm.tab_stride = geom.tab_stride;
+    sm.q_stride = geom.q_stride;
     return sm;
 }
 
@@ -92,17 +95,19 @@ model_eval_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
         bool active = x.in_group && b < a.nconf;
         int nvalid = min(TB, N - TB * x.I);
         double z[TB] = {0., 0., 0., 0.};
-        if (active) load4(a.confs + b * 2 * N, x.I, nvalid, vec_ok, z);
+        if (active) {
+            load4(a.confs + b * 2 * N, x.I, nvalid, vec_ok, z);
+            if (a.state_confs)
+                store4(a.state_confs + b * 2 * N, x.I, nvalid, vec_ok, z);
+        }
         EvalOut o;
         group_eval<LN, EF>(M, sm, x.g, x.I, active, z, nvalid, o);
         if (active) {
             if (EF && a.drift)
                 store4(a.drift + b * N, x.I, nvalid, vec_ok, o.F);
-            if (a.state_confs) {
-                store4(a.state_confs + b * 2 * N, x.I, nvalid, vec_ok, z);
+            if (a.state_confs)
                 store4(a.state_confs + b * 2 * N + N, x.I, nvalid, vec_ok,
                        o.F);
-            }
             if (x.I == 0) {
                 if (LN && a.lnpsi) a.lnpsi[b] = o.lnpsi;
                 if (EF && a.energy) a.energy[b] = o.energy;
@@ -353,7 +358,13 @@ __global__ void dmc_finalize_kernel(DmcBufs B, DmcConsts C, DmcLog L)
 // Reference: evolve_state_inner / evolve_system / ith_diffusion
 // (qmc_base/jastrow/dmc.py:634-673, 743-951), recast (mrbp_qmc/dmc.py:453).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+#ifndef QMCB_STEP_THREADS
+#define QMCB_STEP_THREADS 256
+#endif
+#ifndef QMCB_STEP_MINCTAS
+#define QMCB_STEP_MINCTAS 2
+#endif
+__global__ void __launch_bounds__(QMCB_STEP_THREADS, QMCB_STEP_MINCTAS)
 dmc_step_kernel(const __grid_constant__ DevModel M, GroupGeom geom, DmcBufs B,
                 DmcConsts C)
 {
@@ -397,12 +408,13 @@ dmc_step_kernel(const __grid_constant__ DevModel M, GroupGeom geom, DmcBufs B,
             double zn = zp[c] + 2.0 * fp[c] * C.dt + C.sigma * nrm[c];
             z[c] = recast(zn, C.z_min, C.size);
         }
+        // the new positions are final: write them now, not after the eval
+        store4(nconfs + s * 2 * N, x.I, nvalid, vec_ok, z);
     }
     EvalOut o;
     group_eval<false, true>(M, sm, x.g, x.I, active, z, nvalid, o);
     if (active) {
         double *nc = nconfs + s * 2 * N;
-        store4(nc, x.I, nvalid, vec_ok, z);
         store4(nc + N, x.I, nvalid, vec_ok, o.F);
         if (x.I == 0) {
             double e_parent = penergy[r];
