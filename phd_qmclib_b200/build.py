@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libqmcb200.so')
 SOURCES = ['qmcb_api.cu']
 DEPS = ['qmcb_api.cu', 'qmcb_kernels.cuh', 'qmcb_dev.cuh',
-        'qmcb_estimators.cuh',
+        'qmcb_estimators.cuh', 'qmcb_vmc.cuh',
         os.path.join('..', '..', 'include', 'qmcb200.h')]
 
 NVCC_FLAGS = [

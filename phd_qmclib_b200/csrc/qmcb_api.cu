@@ -14,6 +14,7 @@
 #include "../../include/qmcb200.h"
 #include "qmcb_kernels.cuh"
 #include "qmcb_estimators.cuh"
+#include "qmcb_vmc.cuh"
 
 using namespace qmcb;
 
@@ -118,6 +119,14 @@ struct qmcb_handle {
     double *est_partial = nullptr;              // [CS_BLOCKS][max(3M, B)]
     int *den_hi = nullptr;                      // highest slot count seen
     long long est_log_cap = 0;
+
+    // VMC
+    bool vmc_ready = false;
+    qmcb_vmc_params vp{};
+    VmcState V{};
+    long long vmc_chains = 0, vmc_gstep = 0;
+    int vmc_first = 1;
+    double *vmc_sum_e = nullptr, *vmc_sum_ssf = nullptr, *vmc_acc = nullptr;
 
     // multi-GPU
     ncclComm_t comm = nullptr;
@@ -333,6 +342,17 @@ void free_dmc(qmcb_handle *h)
     h->L = DmcLog{};
     h->log_cap = 0;
     h->dmc_ready = false;
+}
+
+void free_vmc(qmcb_handle *h)
+{
+    cudaFree(h->V.confs); cudaFree(h->V.lnpsi); cudaFree(h->V.eprev);
+    cudaFree(h->V.ssfprev);
+    cudaFree(h->vmc_sum_e); cudaFree(h->vmc_sum_ssf); cudaFree(h->vmc_acc);
+    h->V = VmcState{};
+    h->vmc_sum_e = h->vmc_sum_ssf = h->vmc_acc = nullptr;
+    h->vmc_ready = false;
+    h->vmc_chains = 0;
 }
 
 int alloc_dmc(qmcb_handle *h, const qmcb_dmc_params *p,
@@ -628,6 +648,7 @@ void qmcb_destroy(qmcb_handle *h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     free_dmc(h);
+    free_vmc(h);
     cudaFree(h->d_scratch);
     cudaFree(h->d_counts);
     if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
@@ -1298,24 +1319,148 @@ int qmcb_dmc_rebalance(qmcb_handle *h, int64_t *moved)
     return QMCB_OK;
 }
 
-int qmcb_vmc_init(qmcb_handle *h, const qmcb_vmc_params *, const double *,
-                  int64_t)
+int qmcb_vmc_init(qmcb_handle *h, const qmcb_vmc_params *params,
+                  const double *confs, int64_t num_chains)
 {
     if (!h) return QMCB_ERR_INVALID;
-    FAIL(h, QMCB_ERR_STATE, "qmcb_vmc_init: not implemented yet");
+    if (!params || !confs || num_chains < 1)
+        FAIL(h, QMCB_ERR_INVALID, "bad arguments");
+    if (!(params->upper_bound > params->lower_bound))
+        FAIL(h, QMCB_ERR_INVALID, "upper_bound must exceed lower_bound");
+    if (params->ssf_num_modes < 0 || params->ssf_num_modes > 65536)
+        FAIL(h, QMCB_ERR_INVALID, "bad ssf_num_modes");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int N = h->M.nop, M = params->ssf_num_modes;
+    size_t vsm = (size_t) h->geom.smem_bytes + 8
+                 + (size_t) h->geom.G * h->M.nb * VMC_MB * sizeof(double2);
+    if (vsm > (size_t) h->max_smem)
+        FAIL(h, QMCB_ERR_INVALID, "boson_number too large for the VMC kernel");
+    CUDA_TRY(h, cudaFuncSetAttribute(
+                    vmc_block_kernel,
+                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int) vsm));
+    free_vmc(h);
+    h->vp = *params;
+    const size_t C = (size_t) num_chains;
+    CUDA_TRY(h, cudaMalloc(&h->V.confs, C * 2 * N * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&h->V.lnpsi, C * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&h->V.eprev, C * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&h->vmc_sum_e, C * 2 * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&h->vmc_acc, C * sizeof(double)));
+    if (M) {
+        CUDA_TRY(h, cudaMalloc(&h->V.ssfprev, C * M * 3 * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc(&h->vmc_sum_ssf, C * M * 3 * sizeof(double)));
+        CUDA_TRY(h, cudaMemsetAsync(h->V.ssfprev, 0,
+                                    C * M * 3 * sizeof(double), h->stream));
+    }
+    CUDA_TRY(h, cudaMemsetAsync(h->V.eprev, 0, C * sizeof(double),
+                                h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->V.confs, confs,
+                                C * 2 * N * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+    // Sampling.build_state (mrbp_qmc/vmc.py:145-170): ln|Psi| of the
+    // initial configurations
+    EvalArgs a{};
+    a.confs = h->V.confs; a.nconf = num_chains; a.lnpsi = h->V.lnpsi;
+    int rc = launch_model_eval(h, a, true, false);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->vmc_chains = num_chains;
+    h->vmc_gstep = 0;
+    h->vmc_first = 1;
+    h->vmc_ready = true;
+    return QMCB_OK;
 }
 
-int qmcb_vmc_run_block(qmcb_handle *h, int64_t, double *, double *, uint8_t *,
-                       double *, double *, double *, double *)
+int qmcb_vmc_run_block(qmcb_handle *h, int64_t ns, double *lnpsi,
+                       double *energy, uint8_t *move_stat, double *ssf,
+                       double *accept_rate, double *sum_energy,
+                       double *sum_ssf)
 {
     if (!h) return QMCB_ERR_INVALID;
-    FAIL(h, QMCB_ERR_STATE, "qmcb_vmc_run_block: not implemented yet");
+    if (!h->vmc_ready) FAIL(h, QMCB_ERR_STATE, "qmcb_vmc_init not called");
+    if (ns < 1) FAIL(h, QMCB_ERR_INVALID, "ns must be >= 1");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t C = (size_t) h->vmc_chains;
+    const int M = h->vp.ssf_num_modes;
+    if (ssf && !M) FAIL(h, QMCB_ERR_INVALID, "S(k) estimator is off");
+    // device staging for the optional per-step series
+    size_t n_ser = C * (size_t) ns;
+    size_t bytes = 0;
+    size_t off_ln = bytes; if (lnpsi) bytes += n_ser * sizeof(double);
+    size_t off_e = bytes; if (energy) bytes += n_ser * sizeof(double);
+    size_t off_ssf = bytes; if (ssf) bytes += n_ser * M * 3 * sizeof(double);
+    size_t off_st = bytes; if (move_stat) bytes += n_ser;
+    int rc = ensure_scratch(h, bytes ? bytes : 8);
+    if (rc) return rc;
+    char *scr = reinterpret_cast<char *>(h->d_scratch);
+    VmcArgs a{};
+    a.nchains = h->vmc_chains; a.ns = ns;
+    a.gstep0 = h->vmc_gstep; a.chain_offset = h->vp.chain_offset;
+    a.first = h->vmc_first; a.M = M; a.seed = h->vp.rng_seed;
+    a.spread = h->vp.move_spread; a.z_min = h->vp.lower_bound;
+    a.size = h->vp.upper_bound - h->vp.lower_bound;
+    a.two_over_L = 2.0 / h->M.L;
+    a.out_lnpsi = lnpsi ? reinterpret_cast<double *>(scr + off_ln) : nullptr;
+    a.out_energy = energy ? reinterpret_cast<double *>(scr + off_e) : nullptr;
+    a.out_ssf = ssf ? reinterpret_cast<double *>(scr + off_ssf) : nullptr;
+    a.out_stat = move_stat ? reinterpret_cast<unsigned char *>(scr + off_st)
+                           : nullptr;
+    a.accept_rate = h->vmc_acc;
+    a.sum_energy = h->vmc_sum_e;
+    a.sum_ssf = (M && sum_ssf) ? h->vmc_sum_ssf : nullptr;
+    if (a.sum_ssf)
+        CUDA_TRY(h, cudaMemsetAsync(h->vmc_sum_ssf, 0,
+                                    C * M * 3 * sizeof(double), h->stream));
+    const GroupGeom &g = h->geom;
+    size_t vsm = (size_t) g.smem_bytes + 8
+                 + (size_t) g.G * h->M.nb * VMC_MB * sizeof(double2);
+    long long ctas = ((long long) C + g.G - 1) / g.G;
+    int grid = (int) std::min<long long>(ctas, (long long) h->sm_count * 64);
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    vmc_block_kernel<<<grid, g.nthreads, vsm, h->stream>>>(h->M, g, h->V, a);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    h->vmc_gstep += ns - (h->vmc_first ? 1 : 0);
+    h->vmc_first = 0;
+    h->last_launches = 1;
+    auto d2h = [&](void *dst, const void *src, size_t n) {
+        return cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost,
+                               h->stream);
+    };
+    if (lnpsi) CUDA_TRY(h, d2h(lnpsi, a.out_lnpsi, n_ser * sizeof(double)));
+    if (energy) CUDA_TRY(h, d2h(energy, a.out_energy, n_ser * sizeof(double)));
+    if (ssf) CUDA_TRY(h, d2h(ssf, a.out_ssf, n_ser * M * 3 * sizeof(double)));
+    if (move_stat) CUDA_TRY(h, d2h(move_stat, a.out_stat, n_ser));
+    if (accept_rate)
+        CUDA_TRY(h, d2h(accept_rate, h->vmc_acc, C * sizeof(double)));
+    if (sum_energy)
+        CUDA_TRY(h, d2h(sum_energy, h->vmc_sum_e, C * 2 * sizeof(double)));
+    if (sum_ssf && M)
+        CUDA_TRY(h, d2h(sum_ssf, h->vmc_sum_ssf, C * M * 3 * sizeof(double)));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_total_ms = ms;
+    h->last_step_ms = ms;
+    return QMCB_OK;
 }
 
-int qmcb_vmc_get_state(qmcb_handle *h, double *, double *)
+int qmcb_vmc_get_state(qmcb_handle *h, double *confs, double *lnpsi)
 {
     if (!h) return QMCB_ERR_INVALID;
-    FAIL(h, QMCB_ERR_STATE, "qmcb_vmc_get_state: not implemented yet");
+    if (!h->vmc_ready) FAIL(h, QMCB_ERR_STATE, "qmcb_vmc_init not called");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t C = (size_t) h->vmc_chains;
+    const int N = h->M.nop;
+    if (confs)
+        CUDA_TRY(h, cudaMemcpyAsync(confs, h->V.confs,
+                                    C * 2 * N * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (lnpsi)
+        CUDA_TRY(h, cudaMemcpyAsync(lnpsi, h->V.lnpsi, C * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return QMCB_OK;
 }
 
 }  // extern "C"

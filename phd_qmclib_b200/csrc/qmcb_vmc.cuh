@@ -1,0 +1,200 @@
+// Batched Metropolis VMC: one chain per walker group of a CTA, the whole
+// block of `ns` steps inside one launch (chains never interact).
+//
+// Reference (paths relative to src/phd_qmclib/ of PhD-QMCLib), per chain:
+//   states_generator / blocks          qmc_base/vmc.py:557-648, 670-770
+//   all-particle uniform proposal      qmc_base/jastrow/vmc.py:201-226,
+//                                      mrbp_qmc/vmc.py:206-235
+//   energy / S(k) on acceptance only   qmc_base/jastrow/vmc.py:229-351
+//   momenta k_m = m 2 pi / L, m >= 0   mrbp_qmc/vmc.py:242-271
+#pragma once
+#include "qmcb_kernels.cuh"
+
+namespace qmcb {
+
+constexpr int VMC_MB = 8;       // S(k) modes reduced per CTA barrier pair
+constexpr int VMC_RESEED = 64;  // exact phase re-seed period (modes)
+
+struct VmcState {
+    double *confs;      // [C][2][N]   row 0 positions, row 1 drift
+    double *lnpsi;      // [C]
+    double *eprev;      // [C]         energy of the last accepted state
+    double *ssfprev;    // [C][M][3]   S(k) parts of the last accepted state
+};
+
+struct VmcArgs {
+    long long nchains, ns;
+    long long gstep0;       // generator step index of the first RNG draw
+    long long chain_offset;
+    int first;              // first yielded state = the initial one, ACCEPTED
+    int M;
+    uint64_t seed;
+    double spread, z_min, size, two_over_L;
+    double *out_lnpsi, *out_energy;     // [C][ns] or null
+    unsigned char *out_stat;            // [C][ns] or null
+    double *out_ssf;                    // [C][ns][M][3] or null
+    double *accept_rate;                // [C] or null
+    double *sum_energy;                 // [C][2] (sum e, sum e^2) or null
+    double *sum_ssf;                    // [C][M][3] or null
+};
+
+__global__ void __launch_bounds__(256, 2)
+vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
+                 VmcState S, VmcArgs a)
+{
+    GroupSmem sm = group_smem(geom);
+    GroupIdx x = group_index(M, geom.G);
+    extern __shared__ __align__(16) double qmcb_smem[];
+    // S(k) partials live behind the pair tables: [G][nb][VMC_MB] double2
+    double2 *part_all = reinterpret_cast<double2 *>(
+        qmcb_smem + ((geom.G * (geom.tab_stride + geom.q_stride) + 1) & ~1));
+    const int N = M.nop, nb = M.nb;
+    const bool vec_ok = (N % 2) == 0;
+    const int nvalid = min(TB, N - TB * x.I);
+    for (long long base = (long long) blockIdx.x * geom.G; base < a.nchains;
+         base += (long long) gridDim.x * geom.G) {
+        const long long c = base + x.g;
+        const bool active = x.in_group && c < a.nchains;
+        double z[TB] = {0., 0., 0., 0.}, Fcur[TB] = {0., 0., 0., 0.};
+        double ln_cur = 0.0, e_prev = 0.0, se = 0.0, se2 = 0.0;
+        long long nacc = 0;
+        if (active) {
+            load4(S.confs + c * 2 * N, x.I, nvalid, vec_ok, z);
+            load4(S.confs + c * 2 * N + N, x.I, nvalid, vec_ok, Fcur);
+            ln_cur = S.lnpsi[c];
+            e_prev = S.eprev[c];
+        }
+        const uint32_t gc = (uint32_t) (a.chain_offset + c);
+        double2 *part = part_all + (size_t) x.g * nb * VMC_MB;
+        for (long long st = 0; st < a.ns; ++st) {
+            const bool ini = a.first && st == 0;
+            const long long gs = a.gstep0 + st - (a.first ? 1 : 0);
+            double zp[TB];
+#pragma unroll
+            for (int q = 0; q < TB; ++q) zp[q] = z[q];
+            if (active && !ini) {
+                double u[TB];
+                rng_uniform2(a.seed, gc, (uint32_t) (2 * x.I), (uint32_t) gs,
+                             STREAM_VMC_MOVE, u[0], u[1]);
+                rng_uniform2(a.seed, gc, (uint32_t) (2 * x.I + 1),
+                             (uint32_t) gs, STREAM_VMC_MOVE, u[2], u[3]);
+#pragma unroll
+                for (int q = 0; q < TB; ++q)
+                    zp[q] = recast(z[q] + (u[q] - 0.5) * a.spread, a.z_min,
+                                   a.size);
+            }
+            EvalOut o;
+            group_eval<true, true>(M, sm, x.g, x.I, active, zp, nvalid, o);
+            bool take = false;
+            if (active) {
+                if (ini) {
+                    take = true;
+                } else {
+                    double ua, ub;
+                    rng_uniform2(a.seed, gc, 0u, (uint32_t) gs,
+                                 STREAM_VMC_ACCEPT, ua, ub);
+                    // qmc_base/vmc.py:636
+                    take = o.lnpsi > 0.5 * log(ua) + ln_cur;
+                }
+                if (take) {
+#pragma unroll
+                    for (int q = 0; q < TB; ++q) {
+                        z[q] = zp[q];
+                        Fcur[q] = o.F[q];
+                    }
+                    if (!ini) ln_cur = o.lnpsi;
+                    e_prev = o.energy;
+                    ++nacc;
+                }
+                se += e_prev;
+                se2 = fma(e_prev, e_prev, se2);
+                if (x.I == 0) {
+                    if (a.out_lnpsi) a.out_lnpsi[c * a.ns + st] = ln_cur;
+                    if (a.out_energy) a.out_energy[c * a.ns + st] = e_prev;
+                    if (a.out_stat) a.out_stat[c * a.ns + st] = take ? 1 : 0;
+                }
+            }
+            if (a.M > 0) {
+                // rho_k of the accepted configuration: every thread advances
+                // e^{i k_m z} of its own particles mode by mode; the sum over
+                // the chain's threads goes through shared memory, VMC_MB
+                // modes per barrier pair.
+                double pc[TB], ps[TB], c1[TB], s1[TB], xs[TB];
+#pragma unroll
+                for (int q = 0; q < TB; ++q) {
+                    xs[q] = z[q] * a.two_over_L;
+                    pc[q] = 1.0; ps[q] = 0.0;
+                    c1[q] = 1.0; s1[q] = 0.0;
+                    if (take && q < nvalid) sincospi(xs[q], &s1[q], &c1[q]);
+                }
+                for (int m0 = 0; m0 < a.M; m0 += VMC_MB) {
+                    if (take) {
+                        if (m0 > 0 && (m0 % VMC_RESEED) == 0) {
+#pragma unroll
+                            for (int q = 0; q < TB; ++q)
+                                if (q < nvalid)
+                                    sincospi((double) m0 * xs[q], &ps[q],
+                                             &pc[q]);
+                        }
+                        for (int j = 0; j < VMC_MB; ++j) {
+                            double re = 0.0, im = 0.0;
+#pragma unroll
+                            for (int q = 0; q < TB; ++q) {
+                                if (q < nvalid) { re += pc[q]; im += ps[q]; }
+                                double cn = fma(pc[q], c1[q], -(ps[q] * s1[q]));
+                                ps[q] = fma(ps[q], c1[q], pc[q] * s1[q]);
+                                pc[q] = cn;
+                            }
+                            part[x.I * VMC_MB + j] = make_double2(re, im);
+                        }
+                    }
+                    __syncthreads();
+                    for (int j = x.I; active && j < VMC_MB && m0 + j < a.M;
+                         j += nb) {
+                        const int m = m0 + j;
+                        double *sp = S.ssfprev + (c * a.M + m) * 3;
+                        double v0, v1, v2;
+                        if (take) {
+                            double re = 0.0, im = 0.0;
+                            for (int t = 0; t < nb; ++t) {
+                                double2 pp = part[t * VMC_MB + j];
+                                re += pp.x; im += pp.y;
+                            }
+                            v0 = fma(re, re, im * im); v1 = re; v2 = im;
+                            sp[0] = v0; sp[1] = v1; sp[2] = v2;
+                        } else {
+                            v0 = sp[0]; v1 = sp[1]; v2 = sp[2];
+                        }
+                        if (a.sum_ssf) {
+                            double *ss = a.sum_ssf + (c * a.M + m) * 3;
+                            ss[0] += v0; ss[1] += v1; ss[2] += v2;
+                        }
+                        if (a.out_ssf) {
+                            double *os = a.out_ssf
+                                + ((c * a.ns + st) * a.M + m) * 3;
+                            os[0] = v0; os[1] = v1; os[2] = v2;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        if (active) {
+            store4(S.confs + c * 2 * N, x.I, nvalid, vec_ok, z);
+            store4(S.confs + c * 2 * N + N, x.I, nvalid, vec_ok, Fcur);
+            if (x.I == 0) {
+                S.lnpsi[c] = ln_cur;
+                S.eprev[c] = e_prev;
+                if (a.accept_rate)
+                    a.accept_rate[c] = (double) nacc / (double) a.ns;
+                if (a.sum_energy) {
+                    a.sum_energy[2 * c] = se;
+                    a.sum_energy[2 * c + 1] = se2;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace qmcb

@@ -122,3 +122,119 @@ def test_dmc_capacity_hit(eng_mod, oracle):
     assert rel_err(b['energy'], a['energy']) < 1e-10
     assert eng.dmc_scalars().capacity_hits > 0
     eng.close()
+
+
+@pytest.mark.parametrize('name,nconf,modes', [('lat_n50', 300, 50),
+                                              ('odd_n7', 500, 37),
+                                              ('deep_n200', 40, 400)])
+def test_fourier_density_vs_oracle(eng_mod, oracle, name, nconf, modes):
+    g = golden('model_' + name + '.npz')
+    p = g['params']
+    nop, size = int(p[3]), float(p[4])
+    rng = np.random.default_rng(11)
+    confs = np.zeros((nconf, 2, nop))
+    confs[:, 0] = rng.random((nconf, nop)) * size
+    ref = oracle.fourier_density(p, confs, modes)
+    with eng_mod.Engine((p[:12], p[12:19], p[19:])) as eng:
+        got = eng.fourier_density(confs, modes)
+    # k = 0: |rho|^2 = N^2, Re = N exactly (SURVEY 8c sanity value)
+    assert np.allclose(got[:, 0, 0], nop ** 2, rtol=1e-14)
+    assert np.allclose(got[:, 0, 1], nop, rtol=1e-14)
+    assert np.max(np.abs(got - ref)) < 1e-12 * nop ** 2
+
+
+@pytest.mark.parametrize('name', golden_names('model_'))
+def test_fourier_density_vs_reference(eng_mod, name):
+    g = golden(name)
+    p = g['params']
+    nop = int(p[3])
+    with eng_mod.Engine((p[:12], p[12:19], p[19:])) as eng:
+        got = eng.fourier_density(g['confs'], int(g['num_modes']))
+    assert np.max(np.abs(got - g['ssf'])) < 1e-12 * nop ** 2
+
+
+@pytest.mark.parametrize('pure', [True, False])
+@pytest.mark.parametrize('name,n_ini,wmax,nts,modes,bins', [
+    ('ll_n16', 48, 64, 8, 16, 64), ('lat_n50', 40, 56, 6, 50, 400),
+    ('odd_n7', 64, 96, 9, 21, 33)])
+def test_dmc_estimators_vs_oracle(eng_mod, oracle, name, n_ini, wmax, nts,
+                                  modes, bins, pure):
+    """S(k) and density series of two blocks (forward walking restarts at
+    every block; the window pfw = nts - 2 also exercises plain transport)."""
+    g = golden('model_' + name + '.npz')
+    p = g['params']
+    nop, size = int(p[3]), float(p[4])
+    rng = np.random.default_rng(4)
+    ini = np.zeros((n_ini, 2, nop))
+    ini[:, 0] = rng.random((n_ini, nop)) * size
+    pfw = nts - 2
+    st = oracle.DMCState(p, ini, wmax)
+    ssf = dict(num=modes, pure=pure, pfw=pfw, iter=np.zeros((nts, modes, 3)),
+               aux=np.zeros((2, wmax, modes, 3)))
+    den = dict(num=bins, pure=pure, pfw=pfw, iter=np.zeros((nts, bins)),
+               aux=np.zeros((2, wmax, bins)))
+    eng = eng_mod.Engine((p[:12], p[12:19], p[19:]))
+    dp = eng.dmc_params(2e-3, wmax, n_ini, 0.25, 5, 0.0, size,
+                        ssf=(modes, pure, pfw), density=(bins, pure, pfw))
+    eng.dmc_init(dp, ini)
+    for blk in range(3):
+        est = blk > 0                      # block 0 plays the burn-in role
+        for d in (ssf, den):
+            d['iter'][:] = 0
+            d['aux'][:] = 0
+        a = st.run_block(5, 2e-3, n_ini, 0.25, nts, 0.0, size, eval_est=est,
+                         ssf=ssf, density=den)
+        e_den, e_ssf = np.zeros((nts, bins)), np.zeros((nts, modes, 3))
+        b = eng.dmc_run_block(nts, eval_estimators=est, density=e_den,
+                              ssf=e_ssf)
+        assert np.array_equal(a['num_walkers'], b['num_walkers'])
+        if est:
+            assert np.allclose(e_den, den['iter'], rtol=1e-13, atol=1e-13)
+            assert np.max(np.abs(e_ssf - ssf['iter'])) \
+                < 1e-11 * np.max(np.abs(ssf['iter']))
+    eng.close()
+
+
+@pytest.mark.parametrize('name,nch,ns,modes,spread', [
+    ('ll_n16', 40, 12, 16, 0.5), ('lat_n50', 23, 8, 50, 0.125),
+    ('odd_n7', 64, 16, 11, 0.8), ('defects_n20', 30, 10, 0, 0.2),
+    ('ideal_n8', 16, 10, 8, 0.3)])
+def test_vmc_blocks_vs_oracle(eng_mod, oracle, name, nch, ns, modes, spread):
+    """Same Philox streams: the accept/reject sequence must be identical and
+    every series must agree to rounding, over three consecutive blocks."""
+    g = golden('model_' + name + '.npz')
+    p = g['params']
+    nop, size = int(p[3]), float(p[4])
+    rng = np.random.default_rng(21)
+    ini = np.zeros((nch, 2, nop))
+    ini[:, 0] = rng.random((nch, nop)) * size
+    cur = ini.copy()
+    ln = oracle.model_eval(p, cur, want=('lnpsi',))['lnpsi']
+    eprev = np.zeros(nch)
+    sprev = np.zeros((nch, max(modes, 1), 3))
+    eng = eng_mod.Engine((p[:12], p[12:19], p[19:]))
+    eng.vmc_init(ini, spread, 77, 0.0, size, ssf_num_modes=modes,
+                 chain_offset=5)
+    step0 = 0
+    for b in range(3):
+        first = b == 0
+        a = oracle.vmc_block(p, 77, spread, 0.0, size, cur, ln, eprev,
+                             sprev if modes else None, modes, ns, step0,
+                             first, chain_offset=5)
+        step0 += ns - (1 if first else 0)
+        o = eng.vmc_run_block(ns, series=True, sums=True)
+        assert np.array_equal(o['move_stat'], a['stat'])
+        assert rel_err(o['lnpsi'], a['lnpsi']) < 1e-11
+        assert scaled_err(o['energy'], a['energy']) < 1e-11
+        assert np.allclose(o['accept_rate'], a['accept_rate'], rtol=0,
+                           atol=1e-15)
+        assert np.allclose(o['sum_energy'][:, 0], a['energy'].sum(axis=1),
+                           rtol=1e-11)
+        if modes:
+            assert np.max(np.abs(o['ssf'] - a['ssf'])) < 1e-9
+            assert np.allclose(o['sum_ssf'], a['ssf'].sum(axis=1),
+                               rtol=1e-9, atol=1e-8)
+    confs, lnpsi = eng.vmc_get_state()
+    assert np.allclose(confs[:, 0], cur[:, 0], rtol=0, atol=1e-12)
+    assert rel_err(lnpsi, ln) < 1e-11
+    eng.close()
