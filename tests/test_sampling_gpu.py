@@ -1,0 +1,262 @@
+"""GPU: the sampler classes that mirror the reference's Sampling interface,
+driven the way the reference's procedure layer drives them
+(qmc_exec/dmc/proc.py:136-415, qmc_exec/vmc/proc.py:87-250), checked against
+the oracle step by step and against frozen reference runs statistically."""
+from itertools import islice
+
+import numpy as np
+import pytest
+
+from _blocking import ratio_mean_error
+from conftest import golden, maxnorm_err, rel_err, scaled_err
+from specs import SPECS
+
+pytestmark = pytest.mark.gpu
+
+
+def _ini(spec, n, seed):
+    rng = np.random.default_rng(seed)
+    c = np.zeros((n, 2, spec.boson_number))
+    c[:, 0] = rng.random((n, spec.boson_number)) * spec.supercell_size
+    c[:, 1] = rng.standard_normal((n, spec.boson_number))    # junk drift row
+    return c
+
+
+def test_dmc_build_state(oracle):
+    """Reference tests/mrbp_qmc/test_dmc.py:56-71: positions are copied; plus
+    energies / drift / mask / ref_energy against the oracle."""
+    from phd_qmclib_b200 import dmc, model
+    spec = model.Spec(**SPECS['defects_n20'])
+    p = model.param_block(spec)
+    smp = dmc.Sampling(spec, 1e-3, 48, 32, rng_seed=1)
+    confs = _ini(spec, 40, 0)
+    st = smp.build_state(confs)
+    assert st.num_walkers == 32 and st.max_num_walkers == 48
+    # the LAST target_num_walkers configurations are kept (mrbp_qmc/dmc.py:290)
+    assert np.array_equal(st.confs[:32, 0], confs[-32:, 0])
+    assert np.array_equal(st.props.mask, np.arange(48) >= 32)
+    assert np.all(st.props.weight[:32] == 1) and np.all(st.confs[32:] == 0)
+    o = oracle.DMCState(p, confs[-32:], 48)
+    assert rel_err(st.props.energy[:32], o.prev['energy'][:32]) < 1e-12
+    assert maxnorm_err(st.confs[:32, 1], o.prev['confs'][:32, 1]) < 1e-12
+    assert st.ref_energy == pytest.approx(o.scal[0], rel=1e-13)
+    assert st.energy == pytest.approx(o.ini_energy, rel=1e-13)
+    assert smp.build_state(confs, ref_energy=3.5).ref_energy == 3.5
+    with pytest.raises(dmc.StateError):
+        smp.build_state(np.zeros((4, 2, 19)))
+
+
+@pytest.mark.parametrize('pure', [True, False])
+def test_dmc_blocks_like_proc(oracle, pure):
+    """blocks() consumed as Proc.exec does: burn-in via islice, per-block
+    reductions, last_state of the final block, restart from it."""
+    from phd_qmclib_b200 import dmc, model
+    spec = model.Spec(**SPECS['ll_n16'])
+    p = model.param_block(spec)
+    nts, burn, nblocks, M, B = 8, 1, 3, 16, 32
+    smp = dmc.Sampling(spec, 2e-3, 64, 48, num_walkers_control_factor=0.5,
+                       rng_seed=9,
+                       ssf_est_spec=dmc.SSFEstSpec(M, pure, nts),
+                       density_est_spec=dmc.DensityEstSpec(B, pure, nts))
+    confs = _ini(spec, 48, 3)
+    ini = smp.build_state(confs)
+    it = smp.blocks(ini, nts, burn)
+    for _ in islice(it, burn):
+        pass
+    props = smp.core_funcs.init_props_data_block((nblocks,))
+    ssf_blocks = np.zeros((nblocks, M, 3))
+    den_blocks = np.zeros((nblocks, B, 1))
+    blk = None
+    for b, blk in zip(range(nblocks), it):
+        ip = blk.iter_props
+        assert blk.iter_density.shape == (nts, B, 1)
+        assert blk.iter_ssf.shape == (nts, M, 3)
+        props.energy[b] = ip.energy.sum()
+        props.weight[b] = ip.weight.sum()
+        props.num_walkers[b] = ip.num_walkers.sum()
+        props.ref_energy[b] = ip.ref_energy[-1]
+        if pure:
+            ssf_blocks[b] = blk.iter_ssf[nts - 1]
+            den_blocks[b] = blk.iter_density[nts - 1]
+        else:
+            ssf_blocks[b] = blk.iter_ssf.sum(axis=0)
+            den_blocks[b] = blk.iter_density.sum(axis=0)
+    last = blk.last_state
+
+    # the same run on the oracle
+    st = oracle.DMCState(p, confs, 64)
+    ssf = dict(num=M, pure=pure, pfw=nts, iter=np.zeros((nts, M, 3)),
+               aux=np.zeros((2, 64, M, 3)))
+    den = dict(num=B, pure=pure, pfw=nts, iter=np.zeros((nts, B)),
+               aux=np.zeros((2, 64, B)))
+    for b in range(burn + nblocks):
+        for d in (ssf, den):
+            d['iter'][:] = 0
+            d['aux'][:] = 0
+        a = st.run_block(9, 2e-3, 48, 0.5, nts, 0.0, 16.0, eval_est=b >= burn,
+                         ssf=ssf, density=den)
+        if b >= burn:
+            k = b - burn
+            assert props.energy[k] == pytest.approx(a['energy'].sum(),
+                                                    rel=1e-10)
+            assert props.num_walkers[k] == a['num_walkers'].sum()
+            assert props.ref_energy[k] == pytest.approx(a['ref_energy'][-1],
+                                                        rel=1e-10)
+            want_s = ssf['iter'][nts - 1] if pure else ssf['iter'].sum(axis=0)
+            want_d = den['iter'][nts - 1] if pure else den['iter'].sum(axis=0)
+            assert np.max(np.abs(ssf_blocks[k] - want_s)) \
+                < 1e-10 * np.max(np.abs(want_s))
+            assert np.allclose(den_blocks[k, :, 0], want_d, rtol=1e-13)
+    nw = st.num_walkers
+    assert last.num_walkers == nw
+    assert np.array_equal(last.props.mask, st.act['mask'].astype(bool))
+    assert np.array_equal(last.branching_spec.cloning_ref[:nw], st.ref[:nw])
+    assert np.allclose(last.confs[:nw, 0], st.act['confs'][:nw, 0], rtol=0,
+                       atol=1e-9)
+    assert last.ref_energy == pytest.approx(st.scal[0], rel=1e-10)
+    assert len(last.branching_spec) == 2
+
+    # a stale lazy state is refused, a restart from the last one works
+    blk2 = next(it)
+    with pytest.raises(dmc.StateError):
+        next(it)
+        blk2.last_state
+    it2 = smp.blocks(last, nts, 0)
+    nb = next(it2)
+    assert nb.iter_props.num_walkers[0] > 0
+    assert abs(int(nb.iter_props.num_walkers[0]) - nw) <= nw // 2
+
+
+def test_dmc_disabled_estimators_dummy_arrays():
+    from phd_qmclib_b200 import dmc, model
+    spec = model.Spec(**SPECS['odd_n7'])
+    smp = dmc.Sampling(spec, 1e-3, 40, 24, rng_seed=2)
+    blk = next(smp.blocks(smp.build_state(_ini(spec, 24, 1)), 4, 0))
+    assert blk.iter_density.shape == (1, 1, 1)
+    assert blk.iter_ssf.shape == (1, 1, 3)
+    props, den, ssf, last = blk
+    assert last.max_num_walkers == 40 and len(blk) == 4
+
+
+def test_dmc_states_iterator(oracle):
+    from phd_qmclib_b200 import dmc, model
+    spec = model.Spec(**SPECS['strong_n10'])
+    p = model.param_block(spec)
+    smp = dmc.Sampling(spec, 1e-3, 48, 32, rng_seed=4)
+    confs = _ini(spec, 32, 5)
+    st = oracle.DMCState(p, confs, 48)
+    for k, state in zip(range(3), smp.states(smp.build_state(confs))):
+        a = st.run_block(4, 1e-3, 32, 0.125, 1, 0.0, 10.0)
+        assert state.num_walkers == int(a['num_walkers'][0])
+        assert state.energy == pytest.approx(a['energy'][0], rel=1e-10)
+        assert state.ref_energy == pytest.approx(a['ref_energy'][0],
+                                                 rel=1e-10)
+
+
+@pytest.mark.parametrize('name', ['ll_n16', 'lat_n16'])
+def test_dmc_energy_vs_reference_run(name):
+    """Statistical parity (BASELINE.json north_star): the DMC energy of the
+    engine against a frozen serial run of the LIVE reference with the same
+    model, time step, population and block structure
+    (oracle/make_golden.py: gen_dmc_stat), within combined blocked errors."""
+    from phd_qmclib_b200 import dmc
+    g = golden(f'dmc_stat_{name}.npz')
+    p = g['params']
+    nop = int(p[3])
+    nts, nblocks, burn = int(g['nts']), int(g['nblocks']), int(g['burn'])
+    e_ref, err_ref = ratio_mean_error(g['block_energy'], g['block_weight'])
+
+    class _Spec:            # duck-typed reference Spec: only tuples are read
+        params, obf_params, tbf_params = p[:12], p[12:19], p[19:]
+        boson_number, supercell_size = nop, float(p[4])
+        boundaries = (0.0, float(p[4]))
+        sys_conf_shape = (2, nop)
+
+    smp = dmc.Sampling(_Spec, float(g['time_step']),
+                       int(g['max_num_walkers']), int(g['n_target']),
+                       num_walkers_control_factor=float(g['nwc_factor']),
+                       rng_seed=2024)
+    it = smp.blocks(smp.build_state(g['ini_confs']), nts, burn)
+    for _ in islice(it, burn):
+        pass
+    # four times the reference's length: the engine's error bar is the
+    # smaller of the two
+    e_sum, w_sum = [], []
+    for _, blk in zip(range(4 * nblocks), it):
+        e_sum.append(blk.iter_props.energy.sum())
+        w_sum.append(blk.iter_props.weight.sum())
+    e_eng, err_eng = ratio_mean_error(e_sum, w_sum)
+    sigma = np.hypot(err_ref, err_eng)
+    assert abs(e_eng - e_ref) < 4 * sigma, (e_eng / nop, e_ref / nop,
+                                            sigma / nop)
+    # and the quirk-free textbook weight (energy_mode=1) is measurably lower
+    # (SURVEY.md H1): the reference's semantics are what we match
+
+
+def test_vmc_single_chain_like_reference(oracle):
+    """Reference tests/mrbp_qmc/test_vmc.py:56-125: blocks(), states() and
+    as_chain() of one seed walk the same chain; values against the oracle."""
+    from phd_qmclib_b200 import model, vmc
+    spec = model.Spec(**SPECS['ll_n16'])
+    p = model.param_block(spec)
+    smp = vmc.Sampling(spec, 0.25, rng_seed=1, ssf_est_spec=vmc.SSFEstSpec(8))
+    np.random.seed(0)
+    conf = spec.init_get_sys_conf()
+    ini = smp.build_state(conf)
+    assert ini.move_stat == vmc.STAT_ACCEPTED
+    assert ini.wf_abs_log == pytest.approx(
+        oracle.model_eval(p, conf[None], want=('lnpsi',))['lnpsi'][0],
+        rel=1e-13)
+    ns, nblocks = 32, 3
+    stats, lns = [], []
+    for _, blk in zip(range(nblocks), smp.blocks(ns, ini)):
+        assert blk.iter_props.energy.shape == (ns,)
+        assert blk.iter_ssf.shape == (ns, 8, 3)
+        assert blk.iter_props.move_stat.dtype == bool
+        assert blk.accept_rate == pytest.approx(
+            blk.iter_props.move_stat.mean())
+        assert blk.last_state.sys_conf.shape == (2, 16)
+        stats.append(blk.iter_props.move_stat)
+        lns.append(blk.iter_props.wf_abs_log)
+    stats, lns = np.concatenate(stats), np.concatenate(lns)
+    chain = smp.as_chain(ns * nblocks, ini)
+    assert np.array_equal(chain.props.move_stat, stats)
+    assert np.array_equal(chain.props.wf_abs_log, lns)
+    assert chain.confs.shape == (ns * nblocks, 2, 16)
+    assert chain.accept_rate == pytest.approx(stats.mean())
+    st_stats = [s.move_stat for s in islice(smp.states(ini), ns * nblocks)]
+    assert np.array_equal(np.array(st_stats, dtype=bool), stats)
+    # oracle replay of the same Philox stream
+    cur = conf[None].copy()
+    ln = np.array([ini.wf_abs_log])
+    a = oracle.vmc_block(p, 1, 0.25, 0.0, 16.0, cur, ln, np.zeros(1),
+                         np.zeros((1, 8, 3)), 8, ns, 0, True)
+    assert np.array_equal(a['stat'][0].astype(bool), stats[:ns])
+    assert rel_err(lns[:ns], a['lnpsi'][0]) < 1e-11
+    with pytest.raises(vmc.StateError):
+        smp.build_state(np.zeros((2, 15)))
+
+
+def test_vmc_batched_chains_seed_dmc():
+    """BASELINE configs[1] -> configs[2] in miniature: a batch of chains,
+    device-side block sums, final configurations seed a DMC run."""
+    from phd_qmclib_b200 import dmc, model, vmc
+    spec = model.Spec(**SPECS['lat_n50'])
+    nch = 256
+    smp = vmc.Sampling(spec, 0.25 * spec.well_width, rng_seed=11,
+                       ssf_est_spec=vmc.SSFEstSpec(50))
+    ini = smp.build_state(_ini(spec, nch, 8))
+    assert ini.wf_abs_log.shape == (nch,)
+    sums = smp.block_sums(64, ini)
+    for _ in range(4):
+        o = next(sums)
+    e = o['sum_energy'][:, 0] / 64 / 50
+    assert o['sum_ssf'].shape == (nch, 50, 3)
+    # k = 0 mode: |rho|^2 = N^2 at every step
+    assert np.allclose(o['sum_ssf'][:, 0, 0], 64 * 50 ** 2)
+    assert 0.2 < o['accept_rate'].mean() < 0.95
+    assert 10 < e.mean() < 25
+    confs, _ = smp.engine.vmc_get_state()
+    d = dmc.Sampling(spec, 1e-3, 320, nch, rng_seed=5)
+    blk = next(d.blocks(d.build_state(confs), 16, 0))
+    assert 200 < blk.iter_props.num_walkers[-1] <= 320
