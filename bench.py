@@ -265,8 +265,11 @@ def run_b200(args):
 
     # ---- device-resident timing ------------------------------------------
     eng.set_profiling(True)
+    moved = 0
     for _ in range(args.warmup):
         eng.dmc_advance(nts)
+        if world > 1:
+            eng.dmc_rebalance()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -288,6 +291,9 @@ def run_b200(args):
         launches += st['launches']
         local_ws_list.append(st.get('local_walker_steps', 0))
         ws_local += float(series['num_walkers'].sum())   # GLOBAL when world>1
+        if world > 1:
+            # order-preserving neighbour shifts, once per block, timed
+            moved += eng.dmc_rebalance()
     e1.record(stream)
     barrier(); torch.cuda.synchronize()
     t1 = time.perf_counter()
@@ -356,6 +362,8 @@ def run_b200(args):
                           h_weight[:n_live], sc, slot_energy=h_slot,
                           global_slot_offset=rank * cap)
         eng.dmc_run_block(nts, out=series)
+        if world > 1:
+            eng.dmc_rebalance()
         sc2 = eng.dmc_get_next_into(h_confs, h_energy, h_weight, h_slot)
         return sc2, int(sc2.num_walkers)
 
@@ -398,6 +406,7 @@ def run_b200(args):
             'energy_per_particle_last_step': e_per_particle,
             'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e,
             'gpu_launches': int(launches), 'clocks': clocks,
+            'rebalanced_walkers_rank0': int(moved),
             'lib': os.path.relpath(_lib.LIB_PATH, ROOT),
         }
         print(json.dumps(line), flush=True)

@@ -230,6 +230,16 @@ QMCB_API int qmcb_comm_init(qmcb_handle *h, const uint8_t id[128],
  * neighbours.  Collective call.  moved (may be NULL) = walkers sent. */
 QMCB_API int qmcb_dmc_rebalance(qmcb_handle *h, int64_t *moved);
 
+/* Exchange plan of qmcb_dmc_rebalance, host arithmetic only (no device, no
+ * communicator): counts[world] = live walkers per rank.  For peer p,
+ * send[2p], send[2p+1] = (offset in the caller's current slab, count) of the
+ * walkers p takes over; recv[2p], recv[2p+1] = (offset in the caller's NEW
+ * slab, count) of the walkers p hands over (p == rank: the part that stays).
+ * new_count (may be NULL) = the caller's population afterwards. */
+QMCB_API int qmcb_rebalance_plan(const int64_t *counts, int32_t world,
+                                 int32_t rank, int64_t *send, int64_t *recv,
+                                 int64_t *new_count);
+
 /* ---- VMC ---------------------------------------------------------------- */
 /* Replaces Sampling.build_state (mrbp_qmc/vmc.py:145-170) for num_chains
  * chains: confs [num_chains][2][N]. */

@@ -21,7 +21,7 @@ SYMBOLS = [
     'qmcb_last_block_stats', 'qmcb_measure_fp64_peak', 'qmcb_comm_unique_id', 'qmcb_comm_init',
     'qmcb_dmc_rebalance', 'qmcb_vmc_init', 'qmcb_vmc_run_block',
     'qmcb_vmc_get_state', 'qmcb_measure_fp64_sustained', 'qmcb_stream',
-    'qmcb_host_alloc', 'qmcb_host_free',
+    'qmcb_host_alloc', 'qmcb_host_free', 'qmcb_rebalance_plan',
 ]
 
 
@@ -111,6 +111,7 @@ def load():
     L.qmcb_comm_unique_id.argtypes = [vp]
     L.qmcb_comm_init.argtypes = [vp, vp, i32, i32]
     L.qmcb_dmc_rebalance.argtypes = [vp, C.POINTER(i64)]
+    L.qmcb_rebalance_plan.argtypes = [vp, i32, i32, vp, vp, C.POINTER(i64)]
     L.qmcb_vmc_init.argtypes = [vp, C.POINTER(VMCParams), vp, i64]
     L.qmcb_vmc_run_block.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp]
     L.qmcb_vmc_get_state.argtypes = [vp, vp, vp]

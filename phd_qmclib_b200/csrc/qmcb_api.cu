@@ -778,15 +778,31 @@ int qmcb_dmc_init(qmcb_handle *h, const qmcb_dmc_params *params,
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     double se = 0.0;
     for (int64_t i = 0; i < n; ++i) se += e[i];
+    double n_glob = (double) n, se_glob = se;
+    if (h->comm) {
+        // the initial reference energy is the mean local energy of the
+        // WHOLE ensemble (mrbp_qmc/dmc.py:299-312), identical on every rank
+        double red[2] = {se, (double) n};
+        double *d_red = (double *) ((char *) B.ctl + offsetof(DmcCtl, red));
+        CUDA_TRY(h, cudaMemcpyAsync(d_red, red, sizeof red,
+                                    cudaMemcpyHostToDevice, h->stream));
+        NCCL_TRY(h, nccl_api()->AllReduce(d_red, d_red, 2, ncclDouble,
+                                          ncclSum, h->comm, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(red, d_red, sizeof red,
+                                    cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        se_glob = red[0];
+        n_glob = red[1];
+    }
     DmcCtl ctl{};
     ctl.W_prev = (int) n;
     ctl.W = (int) n;
-    ctl.last_energy = se;
-    ctl.last_weight = (double) n;
-    ctl.last_accum = n > 0 ? se / (double) n : 0.0;
+    ctl.last_energy = se_glob;
+    ctl.last_weight = n_glob;
+    ctl.last_accum = n_glob > 0 ? se_glob / n_glob : 0.0;
     ctl.eref[0] = std::isnan(ref_energy) ? ctl.last_accum : ref_energy;
     ctl.eref[1] = ctl.eref[0];
-    ctl.W_global = (double) n;
+    ctl.W_global = n_glob;
     CUDA_TRY(h, cudaMemcpyAsync(B.ctl, &ctl, sizeof ctl,
                                 cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1200,6 +1216,49 @@ int qmcb_comm_init(qmcb_handle *h, const uint8_t *id, int32_t world_size,
     return QMCB_OK;
 }
 
+// The exchange plan of the order-preserving rebalance, host arithmetic only
+// (exported so that the partition logic can be tested without GPUs).
+// counts[r] = live walkers of rank r.  For peer p:
+//   send[2p], send[2p+1] = (offset in my current slab, n) of walkers p takes
+//   recv[2p], recv[2p+1] = (offset in my NEW slab, n) of walkers p gives me
+// (p == rank describes the part that stays).  new_count = my new population.
+int qmcb_rebalance_plan(const int64_t *counts, int32_t world, int32_t rank,
+                        int64_t *send, int64_t *recv, int64_t *new_count)
+{
+    if (!counts || world < 1 || rank < 0 || rank >= world || !send || !recv)
+        return QMCB_ERR_INVALID;
+    std::vector<long long> cur0(world + 1, 0), new0(world + 1, 0);
+    for (int r = 0; r < world; ++r) {
+        if (counts[r] < 0) return QMCB_ERR_INVALID;
+        cur0[r + 1] = cur0[r] + counts[r];
+    }
+    const long long T = cur0[world];
+    for (int r = 0; r <= world; ++r) new0[r] = T * r / world;
+    auto overlap = [](long long a0, long long a1, long long b0, long long b1,
+                      long long &lo, long long &hi) {
+        lo = a0 > b0 ? a0 : b0;
+        hi = a1 < b1 ? a1 : b1;
+        return hi > lo;
+    };
+    for (int p = 0; p < world; ++p) {
+        long long lo, hi;
+        send[2 * p] = send[2 * p + 1] = 0;
+        recv[2 * p] = recv[2 * p + 1] = 0;
+        if (overlap(cur0[rank], cur0[rank + 1], new0[p], new0[p + 1], lo,
+                    hi)) {
+            send[2 * p] = lo - cur0[rank];
+            send[2 * p + 1] = hi - lo;
+        }
+        if (overlap(cur0[p], cur0[p + 1], new0[rank], new0[rank + 1], lo,
+                    hi)) {
+            recv[2 * p] = lo - new0[rank];
+            recv[2 * p + 1] = hi - lo;
+        }
+    }
+    if (new_count) *new_count = new0[rank + 1] - new0[rank];
+    return QMCB_OK;
+}
+
 // Order-preserving rebalance.  The global ensemble is the
 // concatenation of the ranks' live walkers; the new partition gives rank r
 // the global range [T r / R, T (r + 1) / R).  Every rank sends the parts of
@@ -1231,14 +1290,18 @@ int qmcb_dmc_rebalance(qmcb_handle *h, int64_t *moved)
                                 R * sizeof(long long), cudaMemcpyDeviceToHost,
                                 h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    std::vector<long long> cur0(R + 1, 0), new0(R + 1, 0);
-    for (int r = 0; r < R; ++r) cur0[r + 1] = cur0[r] + cnt[r];
-    const long long T = cur0[R];
-    for (int r = 0; r <= R; ++r) new0[r] = T * r / R;
-    const long long new_n = new0[me + 1] - new0[me];
+    std::vector<int64_t> cnt64(cnt.begin(), cnt.end());
+    std::vector<int64_t> plan_send(2 * R), plan_recv(2 * R);
+    int64_t new_n64 = 0;
+    qmcb_rebalance_plan(cnt64.data(), R, me, plan_send.data(),
+                        plan_recv.data(), &new_n64);
+    const long long new_n = new_n64;
     if (new_n > B.cap) FAIL(h, QMCB_ERR_STATE, "rebalance exceeds capacity");
     bool any = false;
-    for (int r = 0; r < R; ++r) any = any || cur0[r] != new0[r];
+    for (int p = 0; p < R; ++p)
+        any = any || (p != me && (plan_send[2 * p + 1] || plan_recv[2 * p + 1]));
+    // sends and receives pair up rank by rank: a rank whose slab keeps its
+    // walkers has nothing to post
     if (!any) return QMCB_OK;
 
     // staging: [new_n] x (confs, energy, weight)
@@ -1250,20 +1313,13 @@ int qmcb_dmc_rebalance(qmcb_handle *h, int64_t *moved)
     double *s_energy = s_confs + (size_t) new_n * row;
     double *s_weight = s_energy + new_n;
     long long sent = 0;
-    auto overlap = [](long long a0, long long a1, long long b0, long long b1,
-                      long long &lo, long long &hi) {
-        lo = a0 > b0 ? a0 : b0;
-        hi = a1 < b1 ? a1 : b1;
-        return hi > lo;
-    };
     NCCL_TRY(h, api->GroupStart());
     for (int p = 0; p < R; ++p) {
-        long long lo, hi;
         // my current walkers that p will own
-        if (overlap(cur0[me], cur0[me + 1], new0[p], new0[p + 1], lo, hi)) {
-            long long src = lo - cur0[me], n = hi - lo;
+        if (plan_send[2 * p + 1] > 0) {
+            long long src = plan_send[2 * p], n = plan_send[2 * p + 1];
             if (p == me) {
-                long long dst = lo - new0[me];
+                long long dst = plan_recv[2 * p];
                 CUDA_TRY(h, cudaMemcpyAsync(
                                 s_confs + dst * row,
                                 B.confs[par] + src * row,
@@ -1290,9 +1346,8 @@ int qmcb_dmc_rebalance(qmcb_handle *h, int64_t *moved)
             }
         }
         // walkers of p that I will own
-        if (p != me
-            && overlap(cur0[p], cur0[p + 1], new0[me], new0[me + 1], lo, hi)) {
-            long long dst = lo - new0[me], n = hi - lo;
+        if (p != me && plan_recv[2 * p + 1] > 0) {
+            long long dst = plan_recv[2 * p], n = plan_recv[2 * p + 1];
             NCCL_TRY(h, api->Recv(s_confs + dst * row, n * row, ncclDouble, p,
                                   h->comm, h->stream));
             NCCL_TRY(h, api->Recv(s_energy + dst, n, ncclDouble, p, h->comm,
