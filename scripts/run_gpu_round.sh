@@ -10,7 +10,7 @@ timeout 300 python __graft_entry__.py --smoke > $OUT/smoke_$TAG.log 2>&1; tail -
 timeout 900 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; tail -c 3000 $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
 SHORT="python bench.py --steps 1 --warmup 1 --nts 8 --no-cpu"
 timeout 300 $SHORT > $OUT/short_plain_$TAG.log 2>&1 && \
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"dmc_|branch_" -c 300 --csv \
     --log-file $OUT/launches_$TAG.csv $SHORT > $OUT/ncu_launch_$TAG.log 2>&1
 timeout 300 $SHORT > $OUT/short_plain2_$TAG.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:dmc_step -s 9 -c 2 \
