@@ -237,6 +237,8 @@ bool choose_geom(const DevModel &M, int max_smem, GroupGeom &g,
     const int kfull = M.kmax + 1;
     const char *env_kc = getenv("QMCB_KC");
     const char *env_nt = getenv("QMCB_NT");
+    const char *env_il = getenv("QMCB_INTERLEAVE");
+    const bool want_il = !env_il || atoi(env_il) != 0;
     for (int nt = 64; nt <= 256; nt += 32) {
         if (env_nt && atoi(env_nt) != nt) continue;
         int G = nt / M.nb;
@@ -251,7 +253,8 @@ bool choose_geom(const DevModel &M, int max_smem, GroupGeom &g,
             for (int kc = kfull; kc >= 1; kc = (kc > 4 ? (kc + 1) / 2 : kc - 1))
                 kcs.push_back(kc);
         for (int kc : kcs) {
-            int bytes = group_smem_doubles(G, nbp, M.nb, kc) * 8;
+            const bool il = want_il && G > 1 && (G & 1);
+            int bytes = group_smem_doubles(G, nbp, M.nb, kc, il) * 8;
             if (bytes > max_smem) continue;
             int by_smem = (228 * 1024) / (bytes + 1024);
             int ctas = std::min(by_smem, std::min(by_regs, by_thr));
@@ -263,8 +266,9 @@ bool choose_geom(const DevModel &M, int max_smem, GroupGeom &g,
             if (score > best + 1e-9) {
                 best = score;
                 g.nthreads = nt; g.G = G; g.nbp = nbp; g.kc = kc;
-                g.tab_stride = group_tab_stride(nbp, M.nb);
-                g.q_stride = group_q_stride(nbp, M.nb, kc);
+                g.interleave = il ? 1 : 0;
+                g.tab_stride = group_tab_stride(nbp, M.nb, G, il);
+                g.q_stride = group_q_stride(nbp, M.nb, kc, G, il);
                 g.smem_bytes = bytes;
             }
         }

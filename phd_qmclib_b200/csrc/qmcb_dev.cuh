@@ -68,20 +68,33 @@ struct GroupGeom {
     int kc;             // column-sum slots kept in shared memory at a time
     int tab_stride;     // doubles between the table regions of two walkers
     int q_stride;       // doubles between their column-sum regions
+    int interleave;     // thread t -> (walker t % G, block t / G)
     int smem_bytes;
 };
 
-// Lane t = nb g + I of a CTA reads element J of walker g.  With the walker
-// regions spaced so that (stride mod 128 B) equals (nb elements mod 128 B),
-// the lanes of two neighbouring walkers continue each other's bank sequence
-// and a warp that straddles walkers loads without bank conflicts.
-__host__ __device__ inline int bank_aligned_stride(int min_doubles, int nb,
-                                                   int elem_doubles)
+// Bank layout.  A warp reads element J = I + k (mod nb) of walker g for each of
+// its lanes; 8 consecutive lanes form one 128-byte wavefront of a 16-byte
+// access (16 lanes for 8-byte accesses), so consecutive lanes should land in
+// consecutive 16-byte (8-byte) slots modulo 128 bytes.
+//  * contiguous mapping (t = nb g + I): spacing the walker regions by
+//    (nb elements mod 128 B) lets the lanes of the next walker continue the
+//    sequence; the wrap of J inside a walker still costs one extra wavefront.
+//  * interleaved mapping (t = G I + g, G odd): with the walker regions spaced
+//    by s elements, G s = 1 (mod 8 resp. 16), slot(t) = G' t (mod 8/16) with
+//    G' odd: conflict-free, and the wrap of J falls in one wavefront per CTA.
+__host__ __device__ inline int bank_stride(int min_doubles, int want,
+                                           int modulo)
 {
-    int want = (nb * elem_doubles) % 16;
     int s = min_doubles;
-    while (s % 16 != want) ++s;
+    while (s % modulo != want) ++s;
     return s;
+}
+
+__host__ __device__ inline int mod_inverse(int a, int m)
+{
+    for (int x = 1; x < m; ++x)
+        if ((a * x) % m == 1) return x;
+    return 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -208,7 +221,14 @@ __device__ __forceinline__ OneBody one_body(const DevModel &M, double z)
     double zc = z - n_cell;                         // z mod 1, exact
     if (M.za < zc) {                                // barrier
         double arg = M.kp1 * (zc - 1.0 + 0.5 * M.zb);
+#ifndef QMCB_LIBM_TANH
+        // tanh from one exp and one reciprocal: absolute error ~1e-16, which
+        // is what matters for a term added to O(1) drifts and energies
+        double ex = exp(-2.0 * fabs(arg));
+        double th = copysign((1.0 - ex) * fast_rcp(1.0 + ex), arg);
+#else
         double th = tanh(arg);
+#endif
         o.ldz = M.kp1 * th;
         o.kin = -(M.v0 - M.e0) + o.ldz * o.ldz;
         bool defect = (M.defects_sep == 1)
@@ -281,20 +301,27 @@ struct GroupSmem {
     }
 };
 
-__host__ __device__ inline int group_tab_stride(int nbp, int nb)
+__host__ __device__ inline int group_tab_stride(int nbp, int nb, int G,
+                                                bool interleave)
 {
-    return bank_aligned_stride(48 * nbp, nb, 2);
+    // 16-byte elements: slot = doubles / 2, modulo 8 slots
+    int want = interleave ? mod_inverse(G % 8, 8) : nb % 8;
+    return bank_stride(48 * nbp, 2 * want, 16);
 }
 
-__host__ __device__ inline int group_q_stride(int nbp, int nb, int kc)
+__host__ __device__ inline int group_q_stride(int nbp, int nb, int kc, int G,
+                                              bool interleave)
 {
-    return bank_aligned_stride((4 * kc + 2) * nbp, nb, 1);
+    // 8-byte elements, modulo 16 slots
+    int want = interleave ? mod_inverse(G % 16, 16) : nb % 16;
+    return bank_stride((4 * kc + 2) * nbp, want, 16);
 }
 
 __host__ __device__ inline int group_smem_doubles(int G, int nbp, int nb,
-                                                  int kc)
+                                                  int kc, bool interleave)
 {
-    return G * (group_tab_stride(nbp, nb) + group_q_stride(nbp, nb, kc));
+    return G * (group_tab_stride(nbp, nb, G, interleave)
+                + group_q_stride(nbp, nb, kc, G, interleave));
 }
 
 // Result of a walker-group evaluation, per thread.

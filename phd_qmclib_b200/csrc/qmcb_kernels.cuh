@@ -11,13 +11,20 @@ struct GroupIdx {
     bool in_group;      // thread maps to a (walker, block) pair at all
 };
 
-__device__ __forceinline__ GroupIdx group_index(const DevModel &M, int G)
+__device__ __forceinline__ GroupIdx group_index(const DevModel &M,
+                                                const GroupGeom &geom)
 {
     GroupIdx x;
-    int t = threadIdx.x;
-    x.g = t / M.nb;
-    x.I = t - x.g * M.nb;
-    x.in_group = x.g < G;
+    const int t = threadIdx.x, G = geom.G;
+    if (geom.interleave) {
+        x.I = t / G;
+        x.g = t - x.I * G;
+        x.in_group = x.I < M.nb;
+    } else {
+        x.g = t / M.nb;
+        x.I = t - x.g * M.nb;
+        x.in_group = x.g < G;
+    }
     if (!x.in_group) { x.g = 0; x.I = 0; }
     return x;
 }
@@ -86,7 +93,7 @@ model_eval_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                   EvalArgs a)
 {
     GroupSmem sm = group_smem(geom);
-    GroupIdx x = group_index(M, geom.G);
+    GroupIdx x = group_index(M, geom);
     const int N = M.nop;
     const bool vec_ok = (N % 2) == 0;
     for (long long base = (long long) blockIdx.x * geom.G; base < a.nconf;
@@ -382,7 +389,7 @@ dmc_step_kernel(const __grid_constant__ DevModel M, GroupGeom geom, DmcBufs B,
     double *nweight = B.weight[par ^ 1];
 
     GroupSmem sm = group_smem(geom);
-    GroupIdx x = group_index(M, geom.G);
+    GroupIdx x = group_index(M, geom);
     const int N = M.nop;
     const bool vec_ok = (N % 2) == 0;
     const long long s = s0 + x.g;

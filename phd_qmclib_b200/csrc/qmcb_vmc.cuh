@@ -43,7 +43,7 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                  VmcState S, VmcArgs a)
 {
     GroupSmem sm = group_smem(geom);
-    GroupIdx x = group_index(M, geom.G);
+    GroupIdx x = group_index(M, geom);
     extern __shared__ __align__(16) double qmcb_smem[];
     // S(k) partials live behind the pair tables: [G][nb][VMC_MB] double2
     double2 *part_all = reinterpret_cast<double2 *>(
