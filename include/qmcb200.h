@@ -83,13 +83,16 @@ typedef struct {
  * ssf_params).  The engine advances `num_chains` independent chains; chain c
  * is the reference's single-chain algorithm (qmc_base/vmc.py:557-648). */
 typedef struct {
-    double move_spread;
+    double move_spread;             /* proposal 0: width of the uniform move;
+                                       proposal 1: sigma = sqrt(time_step)    */
     double lower_bound;
     double upper_bound;
     uint64_t rng_seed;
     int64_t chain_offset;           /* global index of local chain 0          */
     int32_t ssf_num_modes;          /* 0 = off                                */
-    int32_t reserved0;
+    int32_t proposal;               /* 0: uniform  (qmc_base/vmc.py:401-415);
+                                       1: gaussian (qmc_base/vmc_ndf.py:44-62,
+                                          mrbp_qmc/vmc_ndf.py:24-60)          */
 } qmcb_vmc_params;
 
 /* Scalars of a DMC State (qmc_base/dmc.py:117-127). */

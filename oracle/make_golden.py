@@ -119,6 +119,19 @@ def numba_draws():
                     nor[t, s, i] = np.random.normal(0., 1.)
         return uni, nor
 
+    @nb.njit
+    def draw_vmc_ndf(seed, total, nop):
+        """Replay the gaussian-proposal VMC call sequence: per step nop calls
+        of normal(0, 1) then one rand()."""
+        np.random.seed(seed)
+        out = np.empty((total, nop + 1))
+        for t in range(total):
+            for i in range(nop):
+                out[t, i] = np.random.normal(0., 1.)
+            out[t, nop] = np.random.rand()
+        return out
+
+    draw_uniform.ndf = draw_vmc_ndf
     return draw_uniform, draw_dmc
 
 
@@ -262,12 +275,22 @@ def gen_dmc_blocks(mrbp, name, kwargs, rng, draw_dmc, *, n_ini, wmax, dt,
 
 
 def gen_vmc_blocks(mrbp, name, kwargs, rng, draw_uniform, *, move_spread,
-                   ns, nblocks, num_modes, seed):
+                   ns, nblocks, num_modes, seed, gaussian=False):
+    """gaussian: the vmc_ndf sampler (mrbp_qmc/vmc_ndf.py), `move_spread` is
+    then sigma = sqrt(time_step)."""
     model, vmc = mrbp.model, mrbp.vmc
     spec = model.Spec(**kwargs)
     nop = spec.boson_number
-    sampling = vmc.Sampling(spec, move_spread, rng_seed=seed,
-                            ssf_est_spec=vmc.SSFEstSpec(num_modes))
+    if gaussian:
+        from phd_qmclib.mrbp_qmc import vmc_ndf
+        # attrs field order of the reference class: move_spread (inherited,
+        # unused by the gaussian proposal), model_spec, time_step, ...
+        sampling = vmc_ndf.Sampling(move_spread=move_spread, model_spec=spec,
+                                    time_step=move_spread ** 2, rng_seed=seed,
+                                    ssf_est_spec=vmc.SSFEstSpec(num_modes))
+    else:
+        sampling = vmc.Sampling(spec, move_spread, rng_seed=seed,
+                                ssf_est_spec=vmc.SSFEstSpec(num_modes))
     conf = spec.get_sys_conf_buffer()
     conf[0, :] = rng.random(nop) * spec.supercell_size
     ini_conf = conf.copy()
@@ -283,12 +306,15 @@ def gen_vmc_blocks(mrbp, name, kwargs, rng, draw_uniform, *, move_spread,
         rec['accept_rate'].append(block.accept_rate)
         last = block.last_state
     total = ns * nblocks - 1          # first yield consumes no RNG
-    uni = draw_uniform(seed, total * (nop + 1)).reshape(total, nop + 1)
+    if gaussian:
+        uni = draw_uniform.ndf(seed, total, nop)
+    else:
+        uni = draw_uniform(seed, total * (nop + 1)).reshape(total, nop + 1)
     z_min, z_max = spec.boundaries
     out = dict(params=param_block(spec), ini_conf=ini_conf,
                ini_lnpsi=float(ini_state.wf_abs_log), move_spread=move_spread,
                ns=ns, nblocks=nblocks, num_modes=num_modes, z_min=z_min,
-               z_max=z_max, uniforms=uni,
+               z_max=z_max, uniforms=uni, proposal=int(gaussian),
                last_conf=np.asarray(last.sys_conf),
                last_lnpsi=float(last.wf_abs_log))
     for k, v in rec.items():
@@ -364,6 +390,10 @@ def main():
                        np.random.default_rng(501), draw_uniform,
                        move_spread=0.25 * (1 / 1.5), ns=40, nblocks=2,
                        num_modes=6, seed=6)
+        gen_vmc_blocks(mrbp, 'ndf_lat_n50', SPECS['lat_n50'],
+                       np.random.default_rng(502), draw_uniform,
+                       move_spread=math.sqrt(2e-3), ns=24, nblocks=2,
+                       num_modes=10, seed=7, gaussian=True)
     if 'stat' in which:
         gen_dmc_stat(mrbp, 'll_n16', SPECS['ll_n16'], n_target=512, wmax=640,
                      dt=2e-3, nts=256, nblocks=48, burn=12, seed=11)

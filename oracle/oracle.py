@@ -83,7 +83,7 @@ def lib():
         _f64p, C.c_uint64, C.c_double, C.c_double, C.c_double,
         C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
         _f64p, _f64p, _f64p, opt, C.c_int,
-        _f64p, _f64p, _u8p, opt, _f64p, opt]
+        _f64p, _f64p, _u8p, opt, _f64p, opt, C.c_int]
     L.qmco_vmc_block.restype = None
     L.qmco_num_threads.restype = C.c_int
     L.qmco_set_num_threads.argtypes = [C.c_int]
@@ -276,8 +276,9 @@ def density_step(params, step_idx, confs, num_walkers, wmax, num_bins, pure,
 
 def vmc_block(params, seed, move_spread, z_min, z_max, cur, lnpsi_cur,
               energy_prev, ssf_prev, num_modes, ns, step0, first,
-              chain_offset=0, uniforms_ext=None):
-    """Advance C chains by ns yielded states. cur [C,2,N] is updated."""
+              chain_offset=0, uniforms_ext=None, proposal=0):
+    """Advance C chains by ns yielded states. cur [C,2,N] is updated.
+    proposal: 0 uniform (move_spread = width), 1 gaussian (= sigma)."""
     p = _params(params)
     nch = cur.shape[0]
     out = dict(lnpsi=np.zeros((nch, ns)), energy=np.zeros((nch, ns)),
@@ -291,5 +292,5 @@ def vmc_block(params, seed, move_spread, z_min, z_max, cur, lnpsi_cur,
                          energy_prev, _ptr(ssf_prev), num_modes,
                          out['lnpsi'], out['energy'], out['stat'],
                          _ptr(out['ssf']), out['accept_rate'],
-                         _ptr(uniforms_ext))
+                         _ptr(uniforms_ext), int(proposal))
     return out

@@ -727,8 +727,11 @@ QMCO_API void qmco_dmc_block(const double *p, uint64_t seed,
 /* first != 0: the first yielded state of the chain is the initial one */
 /* flagged ACCEPTED (qmc_base/vmc.py:616-618).                         */
 /* outputs per chain: [C][ns] (+[M][3] for ssf); ssf may be NULL.      */
-/* uniforms_ext, if not NULL: [ns][C][N+1] explicit U[0,1) draws       */
-/* (N proposals then the acceptance one) used instead of Philox.       */
+/* uniforms_ext, if not NULL: [ns][C][N+1] explicit draws (N proposal  */
+/* draws then the U[0,1) acceptance one) used instead of Philox.       */
+/* proposal: 0 = uniform, z + (u - 1/2) move_spread (qmc_base/vmc.py:  */
+/* 401-415); 1 = gaussian, z + N(0, sigma = move_spread)               */
+/* (qmc_base/vmc_ndf.py:44-62; explicit draws are then N(0,1)).        */
 /* ------------------------------------------------------------------ */
 QMCO_API void qmco_vmc_block(const double *p, uint64_t seed,
                              double move_spread, double z_min, double z_max,
@@ -740,7 +743,7 @@ QMCO_API void qmco_vmc_block(const double *p, uint64_t seed,
                              double *out_lnpsi, double *out_energy,
                              uint8_t *out_stat, double *out_ssf,
                              double *accept_rate,
-                             const double *uniforms_ext)
+                             const double *uniforms_ext, int proposal)
 {
     int nop = (int) p[P_NOP];
     double L = p[P_L];
@@ -768,17 +771,24 @@ QMCO_API void qmco_vmc_block(const double *p, uint64_t seed,
                         if (ue) {
                             u0 = ue[2 * q];
                             u1 = (2 * q + 1 < nop) ? ue[2 * q + 1] : 0.;
+                        } else if (proposal == 1) {
+                            rng_normal2(seed, (uint32_t) (chain_offset + c),
+                                        (uint32_t) q, (uint32_t) g, 2u,
+                                        &u0, &u1);
                         } else {
                             rng_uniform2(seed, (uint32_t) (chain_offset + c),
                                          (uint32_t) q, (uint32_t) g, 2u,
                                          &u0, &u1);
                         }
-                        prop[2 * q] = recast_to_supercell(
-                            cc[2 * q] + (u0 - 0.5) * move_spread, z_min, z_max);
+                        double d0 = proposal == 1 ? move_spread * u0
+                                                  : (u0 - 0.5) * move_spread;
+                        double d1 = proposal == 1 ? move_spread * u1
+                                                  : (u1 - 0.5) * move_spread;
+                        prop[2 * q] = recast_to_supercell(cc[2 * q] + d0,
+                                                          z_min, z_max);
                         if (2 * q + 1 < nop)
                             prop[2 * q + 1] = recast_to_supercell(
-                                cc[2 * q + 1] + (u1 - 0.5) * move_spread,
-                                z_min, z_max);
+                                cc[2 * q + 1] + d1, z_min, z_max);
                     }
                     double ln_next = wf_abs_log(prop, p);
                     double ua, ub;

@@ -51,7 +51,7 @@ class VMCParams(C.Structure):
         ('move_spread', C.c_double), ('lower_bound', C.c_double),
         ('upper_bound', C.c_double), ('rng_seed', C.c_uint64),
         ('chain_offset', C.c_int64), ('ssf_num_modes', C.c_int32),
-        ('reserved0', C.c_int32)]
+        ('proposal', C.c_int32)]
 
 
 class StateScalars(C.Structure):

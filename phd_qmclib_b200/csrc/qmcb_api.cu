@@ -1388,6 +1388,9 @@ int qmcb_vmc_init(qmcb_handle *h, const qmcb_vmc_params *params,
         FAIL(h, QMCB_ERR_INVALID, "upper_bound must exceed lower_bound");
     if (params->ssf_num_modes < 0 || params->ssf_num_modes > 65536)
         FAIL(h, QMCB_ERR_INVALID, "bad ssf_num_modes");
+    if (params->proposal != 0 && params->proposal != 1)
+        FAIL(h, QMCB_ERR_INVALID, "proposal must be 0 (uniform) or 1 "
+                                  "(gaussian)");
     CUDA_TRY(h, cudaSetDevice(h->device));
     const int N = h->M.nop, M = params->ssf_num_modes;
     size_t vsm = (size_t) h->geom.smem_bytes + 8
@@ -1456,6 +1459,7 @@ int qmcb_vmc_run_block(qmcb_handle *h, int64_t ns, double *lnpsi,
     a.nchains = h->vmc_chains; a.ns = ns;
     a.gstep0 = h->vmc_gstep; a.chain_offset = h->vp.chain_offset;
     a.first = h->vmc_first; a.M = M; a.seed = h->vp.rng_seed;
+    a.proposal = h->vp.proposal;
     a.spread = h->vp.move_spread; a.z_min = h->vp.lower_bound;
     a.size = h->vp.upper_bound - h->vp.lower_bound;
     a.two_over_L = 2.0 / h->M.L;

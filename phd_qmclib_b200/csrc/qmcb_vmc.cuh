@@ -28,6 +28,7 @@ struct VmcArgs {
     long long chain_offset;
     int first;              // first yielded state = the initial one, ACCEPTED
     int M;
+    int proposal;           // 0 uniform of width `spread`, 1 gaussian sigma
     uint64_t seed;
     double spread, z_min, size, two_over_L;
     double *out_lnpsi, *out_energy;     // [C][ns] or null
@@ -74,14 +75,25 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
             for (int q = 0; q < TB; ++q) zp[q] = z[q];
             if (active && !ini) {
                 double u[TB];
-                rng_uniform2(a.seed, gc, (uint32_t) (2 * x.I), (uint32_t) gs,
-                             STREAM_VMC_MOVE, u[0], u[1]);
-                rng_uniform2(a.seed, gc, (uint32_t) (2 * x.I + 1),
-                             (uint32_t) gs, STREAM_VMC_MOVE, u[2], u[3]);
+                if (a.proposal == 1) {
+                    rng_normal2(a.seed, gc, (uint32_t) (2 * x.I),
+                                (uint32_t) gs, STREAM_VMC_MOVE, u[0], u[1]);
+                    rng_normal2(a.seed, gc, (uint32_t) (2 * x.I + 1),
+                                (uint32_t) gs, STREAM_VMC_MOVE, u[2], u[3]);
 #pragma unroll
-                for (int q = 0; q < TB; ++q)
-                    zp[q] = recast(z[q] + (u[q] - 0.5) * a.spread, a.z_min,
-                                   a.size);
+                    for (int q = 0; q < TB; ++q)
+                        zp[q] = recast(z[q] + a.spread * u[q], a.z_min,
+                                       a.size);
+                } else {
+                    rng_uniform2(a.seed, gc, (uint32_t) (2 * x.I),
+                                 (uint32_t) gs, STREAM_VMC_MOVE, u[0], u[1]);
+                    rng_uniform2(a.seed, gc, (uint32_t) (2 * x.I + 1),
+                                 (uint32_t) gs, STREAM_VMC_MOVE, u[2], u[3]);
+#pragma unroll
+                    for (int q = 0; q < TB; ++q)
+                        zp[q] = recast(z[q] + (u[q] - 0.5) * a.spread,
+                                       a.z_min, a.size);
+                }
             }
             EvalOut o;
             group_eval<true, true>(M, sm, x.g, x.I, active, zp, nvalid, o);

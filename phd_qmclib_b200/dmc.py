@@ -18,7 +18,7 @@ from . import _lib
 from .engine import Engine
 
 __all__ = ['Sampling', 'State', 'StateProps', 'BranchingSpec', 'PropsData',
-           'SamplingBlock', 'DensityEstSpec', 'SSFEstSpec', 'StateError',
+           'SamplingBlock', 'SamplingStateDataBlock', 'DensityEstSpec', 'SSFEstSpec', 'StateError',
            'DDFParams', 'DensityParams', 'SSFParams', 'CFCSpec']
 
 _BIG_NTS = 99999999       # the reference's "very large integer" default
@@ -158,6 +158,13 @@ class SamplingBlock:
         return tuple(self)[i]
 
 
+class SamplingStateDataBlock(t.NamedTuple):
+    """Reference qmc_base/dmc.py:155-159."""
+    confs: np.ndarray
+    props: StateProps
+    iter_props: PropsData
+
+
 class CoreFuncs:
     """The few ``core_funcs`` members the procedure layer touches
     (reference qmc_exec/dmc/proc.py:208-209)."""
@@ -276,11 +283,12 @@ class Sampling:
             self._cache['engine'] = Engine(self.model_spec, self.device)
         return self._cache['engine']
 
-    def _engine_params(self):
+    def _engine_params(self, target_num_walkers=None):
         z_min, z_max = self.model_spec.boundaries
         dp, sp = self.density_params, self.ssf_params
         return Engine.dmc_params(
-            self.time_step, self.max_num_walkers, self.target_num_walkers,
+            self.time_step, self.max_num_walkers,
+            target_num_walkers or self.target_num_walkers,
             self.num_walkers_control_factor, self.rng_seed, z_min, z_max,
             energy_mode=self.energy_mode,
             ssf=None if sp.assume_none else (
@@ -324,7 +332,7 @@ class Sampling:
                      state_weight, n, float(ref_energy), mean_energy, wmax,
                      core_funcs.init_branching_spec(wmax))
 
-    def _load_state(self, ini_state: State):
+    def _load_state(self, ini_state: State, target_num_walkers=None):
         """Ship ``ini_state`` to the GPU as the population to branch from
         (the reference copies it into its three buffers and restarts the
         running totals, qmc_base/dmc.py:700-735)."""
@@ -348,7 +356,8 @@ class Sampling:
         sc.step = 0
         sc.capacity_hits = 0
         self.engine.dmc_set_state(
-            self._engine_params(), np.asarray(ini_state.confs)[:n],
+            self._engine_params(target_num_walkers),
+            np.asarray(ini_state.confs)[:n],
             np.asarray(props.energy)[:n], np.asarray(props.weight)[:n], sc,
             slot_energy=np.asarray(props.energy, dtype=np.float64))
 
@@ -376,6 +385,33 @@ class Sampling:
         while True:
             self.engine.dmc_run_block(1)
             yield self._fetch_state()
+
+    def state_data_blocks(self, ini_state: State, num_time_steps_block: int
+                          ) -> t.Iterator[SamplingStateDataBlock]:
+        """Blocks that keep every State of every step: confs
+        (nts, Wmax, 2, N) and props (nts, Wmax).  Like the reference, the
+        population-control target of this iterator is the initial state's
+        walker count (qmc_base/dmc.py:1009), not ``target_num_walkers``."""
+        nts = int(num_time_steps_block)
+        self._load_state(ini_state, int(ini_state.num_walkers))
+        wmax = self.max_num_walkers
+        while True:
+            confs = np.zeros((nts,) + self.state_confs_shape)
+            energy = np.zeros((nts, wmax))
+            weight = np.zeros((nts, wmax))
+            mask = np.ones((nts, wmax), dtype=bool)
+            props = core_funcs.init_props_data_block((nts,))
+            for i in range(nts):
+                self.engine.dmc_run_block(1)
+                st = self._fetch_state()
+                confs[i], energy[i] = st.confs, st.props.energy
+                weight[i], mask[i] = st.props.weight, st.props.mask
+                props.energy[i], props.weight[i] = st.energy, st.weight
+                props.num_walkers[i] = st.num_walkers
+                props.ref_energy[i] = st.ref_energy
+                props.accum_energy[i] = st.accum_energy
+            yield SamplingStateDataBlock(
+                confs, StateProps(energy, weight, mask), props)
 
     def blocks(self, ini_state: State, num_time_steps_blocks: int,
                burn_in_blocks: int) -> t.Iterator[SamplingBlock]:

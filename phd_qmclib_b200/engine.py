@@ -309,7 +309,7 @@ class Engine:
 
     # -- VMC ----------------------------------------------------------------
     def vmc_init(self, confs, move_spread, rng_seed, lower_bound,
-                 upper_bound, ssf_num_modes=0, chain_offset=0):
+                 upper_bound, ssf_num_modes=0, chain_offset=0, proposal=0):
         confs = _f64(confs)
         if confs.ndim == 2:
             confs = confs[None]
@@ -319,6 +319,7 @@ class Engine:
         p.rng_seed = int(rng_seed) & 0xFFFFFFFFFFFFFFFF
         p.chain_offset = chain_offset
         p.ssf_num_modes = ssf_num_modes
+        p.proposal = proposal
         rc = self._L.qmcb_vmc_init(self._h, C.byref(p), ptr(confs),
                                    confs.shape[0])
         self._check(rc, 'qmcb_vmc_init')

@@ -172,16 +172,25 @@ class Sampling:
         return State(sys_conf, ln,
                      np.full(len(ln), STAT_ACCEPTED, dtype=np.int64))
 
+    #: 0 = uniform proposal of width ``move_spread``; the gaussian variant
+    #: (``vmc_ndf.Sampling``) overrides both
+    _proposal = 0
+
+    def _proposal_scale(self):
+        return self.move_spread
+
     def _start(self, ini_state: State):
         conf = np.asarray(ini_state.sys_conf, dtype=np.float64)
         single = conf.ndim == 2
         z_min, z_max = self.model_spec.boundaries
         sp = self.ssf_params
-        self.engine.vmc_init(conf[None] if single else conf, self.move_spread,
-                             self.rng_seed, z_min, z_max,
+        self.engine.vmc_init(conf[None] if single else conf,
+                             self._proposal_scale(), self.rng_seed, z_min,
+                             z_max,
                              ssf_num_modes=0 if sp.assume_none
                              else sp.num_modes,
-                             chain_offset=self.chain_offset)
+                             chain_offset=self.chain_offset,
+                             proposal=self._proposal)
         return single
 
     def _last_state(self, single, stat_last) -> State:
@@ -230,14 +239,18 @@ class Sampling:
             o = self.engine.vmc_run_block(1, series=True)
             yield self._last_state(single, o['move_stat'][:, -1])
 
-    def as_chain(self, num_steps: int,
-                 ini_state: State) -> SamplingStateDataBlock:
-        """The chain with every configuration kept, e.g. to seed a DMC run
-        (reference qmc_base/vmc.py:215-229, 773-902)."""
-        ns = int(num_steps)
+    def state_data_blocks(self, num_steps_block: int, ini_state: State
+                          ) -> t.Iterator[SamplingStateDataBlock]:
+        """Blocks that keep every configuration
+        (reference qmc_base/vmc.py:848-902)."""
+        ns = int(num_steps_block)
         single = self._start(ini_state)
         nop = self.model_spec.boson_number
         nch = 1 if single else len(ini_state.sys_conf)
+        while True:
+            yield self._chain_block(ns, single, nch, nop)
+
+    def _chain_block(self, ns, single, nch, nop):
         confs = np.zeros((nch, ns, 2, nop))
         ln = np.zeros((nch, ns)); en = np.zeros((nch, ns))
         stat = np.zeros((nch, ns), dtype=np.bool_)
@@ -255,3 +268,13 @@ class Sampling:
                 last)
         return SamplingStateDataBlock(confs, PropsData(ln, en, stat), acc,
                                       last)
+
+    def as_chain(self, num_steps: int,
+                 ini_state: State) -> SamplingStateDataBlock:
+        """The chain with every configuration kept, e.g. to seed a DMC run
+        (reference qmc_base/vmc.py:215-229, 773-902)."""
+        ns = int(num_steps)
+        single = self._start(ini_state)
+        nop = self.model_spec.boson_number
+        nch = 1 if single else len(ini_state.sys_conf)
+        return self._chain_block(ns, single, nch, nop)

@@ -195,11 +195,13 @@ def test_dmc_estimators_vs_oracle(eng_mod, oracle, name, n_ini, wmax, nts,
     eng.close()
 
 
-@pytest.mark.parametrize('name,nch,ns,modes,spread', [
-    ('ll_n16', 40, 12, 16, 0.5), ('lat_n50', 23, 8, 50, 0.125),
-    ('odd_n7', 64, 16, 11, 0.8), ('defects_n20', 30, 10, 0, 0.2),
-    ('ideal_n8', 16, 10, 8, 0.3)])
-def test_vmc_blocks_vs_oracle(eng_mod, oracle, name, nch, ns, modes, spread):
+@pytest.mark.parametrize('name,nch,ns,modes,spread,proposal', [
+    ('ll_n16', 40, 12, 16, 0.5, 0), ('lat_n50', 23, 8, 50, 0.125, 0),
+    ('odd_n7', 64, 16, 11, 0.8, 0), ('defects_n20', 30, 10, 0, 0.2, 0),
+    ('ideal_n8', 16, 10, 8, 0.3, 0), ('lat_n50', 23, 8, 10, 0.05, 1),
+    ('frac_n21', 31, 9, 5, 0.1, 1)])
+def test_vmc_blocks_vs_oracle(eng_mod, oracle, name, nch, ns, modes, spread,
+                              proposal):
     """Same Philox streams: the accept/reject sequence must be identical and
     every series must agree to rounding, over three consecutive blocks."""
     g = golden('model_' + name + '.npz')
@@ -214,13 +216,13 @@ def test_vmc_blocks_vs_oracle(eng_mod, oracle, name, nch, ns, modes, spread):
     sprev = np.zeros((nch, max(modes, 1), 3))
     eng = eng_mod.Engine((p[:12], p[12:19], p[19:]))
     eng.vmc_init(ini, spread, 77, 0.0, size, ssf_num_modes=modes,
-                 chain_offset=5)
+                 chain_offset=5, proposal=proposal)
     step0 = 0
     for b in range(3):
         first = b == 0
         a = oracle.vmc_block(p, 77, spread, 0.0, size, cur, ln, eprev,
                              sprev if modes else None, modes, ns, step0,
-                             first, chain_offset=5)
+                             first, chain_offset=5, proposal=proposal)
         step0 += ns - (1 if first else 0)
         o = eng.vmc_run_block(ns, series=True, sums=True)
         assert np.array_equal(o['move_stat'], a['stat'])

@@ -123,7 +123,9 @@ def test_vmc_blocks(oracle, name):
         out = oracle.vmc_block(g['params'], 0, float(g['move_spread']),
                                float(g['z_min']), float(g['z_max']), cur, ln,
                                eprev, sprev, nm, ns, 0, first,
-                               uniforms_ext=ue[:, None, :])
+                               uniforms_ext=ue[:, None, :],
+                               proposal=int(g['proposal'])
+                               if 'proposal' in g.files else 0)
         assert np.array_equal(out['stat'][0].astype(bool), g['it_stat'][b])
         assert rel_err(out['lnpsi'][0], g['it_lnpsi'][b]) < 1e-12
         assert rel_err(out['energy'][0], g['it_energy'][b]) < 1e-11

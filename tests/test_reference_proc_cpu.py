@@ -92,10 +92,10 @@ class OracleEngine:
 
     # -- VMC ------------------------------------------------------------
     def vmc_init(self, confs, move_spread, rng_seed, lower, upper,
-                 ssf_num_modes=0, chain_offset=0):
+                 ssf_num_modes=0, chain_offset=0, proposal=0):
         self.v = dict(cur=np.array(confs, dtype=np.float64), spread=move_spread,
                       seed=rng_seed, lo=lower, hi=upper, M=ssf_num_modes,
-                      off=chain_offset, step0=0, first=True)
+                      off=chain_offset, step0=0, first=True, prop=proposal)
         c = len(confs)
         self.v['ln'] = self.o.model_eval(self.p, self.v['cur'],
                                          want=('lnpsi',))['lnpsi']
@@ -107,7 +107,8 @@ class OracleEngine:
         a = self.o.vmc_block(self.p, v['seed'], v['spread'], v['lo'],
                              v['hi'], v['cur'], v['ln'], v['e'],
                              v['s'] if v['M'] else None, v['M'], ns,
-                             v['step0'], v['first'], chain_offset=v['off'])
+                             v['step0'], v['first'], chain_offset=v['off'],
+                             proposal=v['prop'])
         v['step0'] += ns - (1 if v['first'] else 0)
         v['first'] = False
         return dict(lnpsi=a['lnpsi'], energy=a['energy'],

@@ -260,3 +260,52 @@ def test_vmc_batched_chains_seed_dmc():
     d = dmc.Sampling(spec, 1e-3, 320, nch, rng_seed=5)
     blk = next(d.blocks(d.build_state(confs), 16, 0))
     assert 200 < blk.iter_props.num_walkers[-1] <= 320
+
+
+def test_state_data_blocks():
+    """Reference tests/mrbp_qmc/test_dmc.py:118-136 / test_vmc.py: blocks
+    that keep every state."""
+    from phd_qmclib_b200 import dmc, model, vmc
+    spec = model.Spec(**SPECS['odd_n7'])
+    d = dmc.Sampling(spec, 1e-3, 40, 24, rng_seed=3)
+    ini = d.build_state(_ini(spec, 24, 2))
+    blk = next(d.state_data_blocks(ini, 5))
+    assert blk.confs.shape == (5, 40, 2, 7)
+    assert blk.props.energy.shape == (5, 40) and blk.props.mask.dtype == bool
+    nw = blk.iter_props.num_walkers
+    for i in range(5):
+        assert (~blk.props.mask[i]).sum() == nw[i]
+        assert blk.iter_props.energy[i] == pytest.approx(
+            blk.props.energy[i, :int(nw[i])].sum(), rel=1e-12)
+    v = vmc.Sampling(spec, 0.4, rng_seed=8)
+    vini = v.build_state(_ini(spec, 1, 4)[0])
+    vb = next(v.state_data_blocks(6, vini))
+    assert vb.confs.shape == (6, 2, 7) and vb.props.energy.shape == (6,)
+    # rejected steps repeat the configuration
+    for i in range(1, 6):
+        if not vb.props.move_stat[i]:
+            assert np.array_equal(vb.confs[i, 0], vb.confs[i - 1, 0])
+
+
+def test_vmc_gaussian_proposal_sampler(oracle):
+    """vmc_ndf.Sampling (reference mrbp_qmc/vmc_ndf.py): sigma =
+    sqrt(time_step); chain against the oracle's gaussian-proposal replay."""
+    from phd_qmclib_b200 import model, vmc_ndf
+    spec = model.Spec(**SPECS['lat_n50'])
+    p = model.param_block(spec)
+    smp = vmc_ndf.Sampling(model_spec=spec, time_step=2e-3, rng_seed=3,
+                           ssf_est_spec=vmc_ndf.SSFEstSpec(6))
+    assert smp.tpf_params.sigma == pytest.approx(np.sqrt(2e-3))
+    conf = _ini(spec, 1, 6)[0]
+    ini = smp.build_state(conf)
+    blk = next(smp.blocks(20, ini))
+    cur = conf[None].copy()
+    cur[:, 1] = 0
+    ln = np.array([ini.wf_abs_log])
+    a = oracle.vmc_block(p, 3, np.sqrt(2e-3), 0.0, 50.0, cur, ln, np.zeros(1),
+                         np.zeros((1, 6, 3)), 6, 20, 0, True, proposal=1)
+    assert np.array_equal(blk.iter_props.move_stat, a['stat'][0].astype(bool))
+    assert rel_err(blk.iter_props.wf_abs_log, a['lnpsi'][0]) < 1e-11
+    assert scaled_err(blk.iter_props.energy, a['energy'][0]) < 1e-11
+    with pytest.raises(TypeError):
+        vmc_ndf.Sampling(model_spec=spec)
