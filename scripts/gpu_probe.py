@@ -30,15 +30,18 @@ for nop, L, rm in [(100, 100.0, 25.0), (21, 17.5, 1.75), (7, 10.0, 3.3)]:
           f'{sc(o["energy"], r["energy"]):.2e} drift '
           f'{np.max(np.abs(o["drift"] - r["drift"])) / np.max(np.abs(r["drift"])):.2e}')
 
-cases = [(100, 125000), (50, 100000), (200, 20000), (20, 100000)]
+cases = [(100, 125000, False), (50, 100000, False), (200, 20000, False),
+         (20, 100000, False)]
 if len(sys.argv) > 1:
-    cases = [(100, 125000)]
-for nop, nw in cases:
+    cases = [(100, 125000, False), (100, 125000, True)]
+for nop, nw, shuffled in cases:
     spec = model.Spec(5 * PI ** 2, 1, 2, nop, nop, 0.25 * nop)
     eng = engine.Engine(spec)
     rng = np.random.default_rng(0)
     ini = np.zeros((nw, 2, nop))
     ini[:, 0] = np.arange(nop)[None, :] + 0.25 + 0.15 * (rng.random((nw, nop)) - 0.5)
+    if shuffled:        # same physics, particle labels in random order
+        ini[:, 0] = rng.permuted(ini[:, 0], axis=1)
     cap = int(nw * 1.25)
     dp = eng.dmc_params(6.25e-4, cap, nw, 0.5, 7, 0.0, float(nop))
     eng.dmc_init(dp, ini)
@@ -49,7 +52,7 @@ for nop, nw in cases:
     st = eng.last_block_stats()
     ws = float(out['num_walkers'].sum())
     F = 58 * nop * (nop - 1) / 2 + 113 * nop + 35
-    print(f'N={nop} W={nw} KC={os.environ.get("QMCB_KC")} NT={os.environ.get("QMCB_NT")}: '
+    print(f'N={nop} W={nw} shuffled={shuffled} KC={os.environ.get("QMCB_KC")} NT={os.environ.get("QMCB_NT")}: '
           f'block {st["total_ms"]:.2f} ms step-kernel {st["step_kernel_ms"]:.2f} ms  '
           f'{ws / (st["total_ms"] * 1e-3):.3e} ws/s  '
           f'alg {ws * F / (st["step_kernel_ms"] * 1e-3) / 1e12:.2f} TF  '
