@@ -211,7 +211,7 @@ bool build_model(const qmcb_model_params &p, DevModel &M, std::string &err)
     // near-branch units (qmcb_dev.cuh): drift in -k2, kinetic in k2^2
     double gam = M.is_ideal ? 1.0 : (M_PI / M.L) * std::sqrt(beta) / k2;
     M.inv_gam = 1.0 / gam;
-    M.mu_over_gam = M.is_ideal ? 0.0 : -(M_PI / M.L) * beta / (k2 * gam);
+    M.mu = M.is_ideal ? 0.0 : -(M_PI / M.L) * beta / k2;
     M.s_m_scaled = s_m / gam;
     M.ln_gam = std::log(gam);
     M.drift_unit = M.is_ideal ? 1.0 : -k2;
@@ -232,8 +232,9 @@ bool choose_geom(const DevModel &M, int max_smem, GroupGeom &g,
                  std::string &err)
 {
     const int regs_per_thread = 128;
+    const char *env_odd = getenv("QMCB_ODD_ROWS");
+    const int nbp = (env_odd && atoi(env_odd)) ? M.nb : M.nb + (M.nb & 1);
     double best = -1.0;
-    const int nbp = M.nb + (M.nb & 1);
     const int kfull = M.kmax + 1;
     const char *env_kc = getenv("QMCB_KC");
     const char *env_nt = getenv("QMCB_NT");

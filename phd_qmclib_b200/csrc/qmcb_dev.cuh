@@ -51,7 +51,7 @@ struct DevModel {
     double beta, ln_am, k2;
     double k2_over_pi;
     double inv_gam;                   // 1/gamma_f, gamma_f = (pi/L) sqrt(beta)/k2
-    double mu_over_gam;               // -(pi/L) beta / (k2 gamma_f)
+    double mu;                        // -(pi/L) beta / k2
     double s_m_scaled;                // sin(pi r_m / L) / gamma_f
     double ln_gam;                    // ln gamma_f
     double cpsi[2], spsi[2];          // cos/sin(psi_w)
@@ -257,16 +257,23 @@ __device__ __forceinline__ void particle_tables(const DevModel &M, double z,
 
 // ---------------------------------------------------------------------------
 // Shared-memory view of one CTA: G walkers, each with (nbp doubles per row)
-//   A1  [4][nbp] double2   (sin a_j, cos a_j) / gamma_f         far den
-//   A2  [4][nbp] double2   (sin a_j, cos a_j) mu_f / gamma_f    far num
+//   A1  [4][nbp] double2   (sin a_j, cos a_j) / gamma_f   far branch
 //   V   [4 variants][4][nbp] double2  (sin, cos)(u_j + sigma psi_w)
-//   Q   [kc][4][nbp]       column partial sums of the drift
-//   red [2][nbp]           per-thread partials of E_L and ln|Psi|
+//   Q   [kc][4][nbp]       column partial sums of the drift; its first two
+//                          rows double as the per-thread partials of E_L and
+//                          ln|Psi| in the final reduction
 // Particle p = 4 J + c is stored at [..][c][J]: the threads of a walker walk
 // J, so accesses are unit-stride across lanes.  nbp is even, which makes the
 // variant stride a multiple of 128 bytes: lanes that pick different variants
 // still hit distinct banks.
 // ---------------------------------------------------------------------------
+// Rows per walker: far table 8 + variants 32; the final reductions reuse the
+// column-sum rows.  (A second, pre-scaled copy of the far table would save
+// one multiply per pair but costs more in shared-memory traffic and in
+// column-sum slots than it gains: measured -4 %.)
+constexpr int TAB_ROWS = 40;
+constexpr int RED_ROWS = 0;
+
 struct GroupSmem {
     double *base;
     int nbp, kc, G, tab_stride, q_stride;
@@ -282,13 +289,9 @@ struct GroupSmem {
     {
         return reinterpret_cast<double2 *>(tab(g)) + c * nbp;
     }
-    __device__ __forceinline__ double2 *a2(int g, int c) const
-    {
-        return reinterpret_cast<double2 *>(tab(g) + 8 * nbp) + c * nbp;
-    }
     __device__ __forceinline__ double2 *var(int g, int v, int c) const
     {
-        return reinterpret_cast<double2 *>(tab(g) + 16 * nbp)
+        return reinterpret_cast<double2 *>(tab(g) + (TAB_ROWS - 32) * nbp)
                + (v * 4 + c) * nbp;
     }
     __device__ __forceinline__ double *q(int g, int k, int c) const
@@ -297,7 +300,7 @@ struct GroupSmem {
     }
     __device__ __forceinline__ double *red(int g, int which) const
     {
-        return qreg(g) + (4 * kc + which) * nbp;
+        return qreg(g) + which * nbp;       // after the last column-sum fold
     }
 };
 
@@ -306,7 +309,7 @@ __host__ __device__ inline int group_tab_stride(int nbp, int nb, int G,
 {
     // 16-byte elements: slot = doubles / 2, modulo 8 slots
     int want = interleave ? mod_inverse(G % 8, 8) : nb % 8;
-    return bank_stride(48 * nbp, 2 * want, 16);
+    return bank_stride(TAB_ROWS * nbp + ((TAB_ROWS * nbp) & 1), 2 * want, 16);
 }
 
 __host__ __device__ inline int group_q_stride(int nbp, int nb, int kc, int G,
@@ -314,7 +317,7 @@ __host__ __device__ inline int group_q_stride(int nbp, int nb, int kc, int G,
 {
     // 8-byte elements, modulo 16 slots
     int want = interleave ? mod_inverse(G % 16, 16) : nb % 16;
-    return bank_stride((4 * kc + 2) * nbp, want, 16);
+    return bank_stride((4 * kc + RED_ROWS) * nbp, want, 16);
 }
 
 __host__ __device__ inline int group_smem_doubles(int G, int nbp, int nb,
@@ -354,12 +357,11 @@ __device__ __forceinline__ void pair_tile(
     const int cstride = nbp * (int) sizeof(double2);    // next column particle
     const unsigned vstride = 4u * (unsigned) cstride;   // next variant
     const char *pa1 = reinterpret_cast<const char *>(sm.a1(g, 0) + J);
-    const char *pa2 = reinterpret_cast<const char *>(sm.a2(g, 0) + J);
     const char *pv = reinterpret_cast<const char *>(sm.var(g, 0, 0) + J);
     double *pq = sm.q(g, qslot, 0) + J;
     const double s_m = M.s_m_scaled;
     double2 A1 = *reinterpret_cast<const double2 *>(pa1);
-    double2 A2 = *reinterpret_cast<const double2 *>(pa2);
+    const double mu = M.mu;
 #pragma unroll 1
     for (int c2 = 0; c2 < TB; ++c2) {
         // phase 1: far branch in near units for the four rows,
@@ -372,7 +374,7 @@ __device__ __forceinline__ void pair_tile(
 #pragma unroll
         for (int c1 = 0; c1 < TB; ++c1) {
             den_f[c1] = fma(rsa[c1], A1.y, -(rca[c1] * A1.x));
-            num_f[c1] = fma(rca[c1], A2.y, rsa[c1] * A2.x);
+            num_f[c1] = mu * fma(rca[c1], A1.y, rsa[c1] * A1.x);
         }
 #pragma unroll
         for (int c1 = 0; c1 < TB; ++c1) {
@@ -383,9 +385,8 @@ __device__ __forceinline__ void pair_tile(
         }
         // next column particle's far tables, in flight during phase 2
         if (c2 + 1 < TB) {
-            pa1 += cstride; pa2 += cstride;
+            pa1 += cstride;
             A1 = *reinterpret_cast<const double2 *>(pa1);
-            A2 = *reinterpret_cast<const double2 *>(pa2);
         }
         pv += cstride;
         // phase 2: near branch, select, one reciprocal per pair
@@ -469,8 +470,6 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
             if (!M.is_ideal) {
                 sm.a1(g, c)[I] = make_double2(rsa[c] * M.inv_gam,
                                               rca[c] * M.inv_gam);
-                sm.a2(g, c)[I] = make_double2(rsa[c] * M.mu_over_gam,
-                                              rca[c] * M.mu_over_gam);
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     // v = 2 * unwrapped + (sigma > 0); u_j' = u_j + sigma psi
@@ -520,7 +519,7 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
                         Tq[c] += sm.q(g, k - k0, c)[I];
                 }
             }
-            if (k1 <= kmax) __syncthreads();
+            __syncthreads();    // the reductions below reuse these rows
         }
     }
     if (!EF) __syncthreads();
