@@ -924,10 +924,9 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
     for (int64_t i = 0; i < nts; ++i) {
         branch_count_kernel<<<B.nblk, BR_THREADS, 0, h->stream>>>(B, h->C);
-        branch_scan_kernel<<<1, BR_THREADS, 0, h->stream>>>(B);
-        branch_fill_kernel<<<B.nblk, BR_THREADS, 0, h->stream>>>(B);
-        dmc_local_sum_kernel<<<1, BR_THREADS, 0, h->stream>>>(B);
-        if (h->comm)
+        branch_fill_kernel<<<B.nblk, BR_THREADS, 0, h->stream>>>(
+            B, h->C, L, h->comm ? 0 : 1);
+        if (h->comm) {
             // population control needs the GLOBAL {sum E, W}
             // (qmc_base/dmc.py:758-771); 16 bytes, in place
             NCCL_TRY(h, nccl_api()->AllReduce(
@@ -935,6 +934,8 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
                                             + offsetof(DmcCtl, red)),
                             (void *) ((char *) B.ctl + offsetof(DmcCtl, red)),
                             2, ncclDouble, ncclSum, h->comm, h->stream));
+            dmc_finalize_kernel<<<1, 32, 0, h->stream>>>(B, h->C, L);
+        }
         if (h->profile_steps)
             CUDA_TRY(h, cudaEventRecord(h->step_ev[2 * i], h->stream));
         dmc_step_kernel<<<step_grid, g.nthreads, g.smem_bytes, h->stream>>>(
@@ -951,12 +952,11 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
             if (rc) return rc;
             est_launches += 3;
         }
-        dmc_finalize_kernel<<<1, 32, 0, h->stream>>>(B, h->C, L);
     }
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     h->step_host += nts;
-    h->last_launches = (6 + (h->comm ? 1 : 0)) * nts + est_launches;
+    h->last_launches = (3 + (h->comm ? 2 : 0)) * nts + est_launches;
     if (density && do_den)
         CUDA_TRY(h, cudaMemcpyAsync(density, h->den_iter,
                                     nts * (size_t) NB * sizeof(double),

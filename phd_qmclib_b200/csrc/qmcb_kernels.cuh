@@ -141,6 +141,8 @@ struct DmcCtl {
     double red[2];              // {sum E_parents, W}: local, then global
     double last_energy, last_weight, last_accum;
     double W_global;            // global live walkers of the last step
+    unsigned int done_count;    // CTAs of branch_count_kernel that finished
+    unsigned int done_fill;     // CTAs of branch_fill_kernel that finished
 };
 
 struct DmcBufs {
@@ -208,7 +210,51 @@ __device__ __forceinline__ long long block_excl_scan(long long v,
     return r;
 }
 
-// K4a: clone counts c_s = int(w_s + u_s) (qmc_base/dmc.py:641-643).
+// Scan of the per-CTA sums (one CTA); fixes W for this step.
+__device__ __forceinline__ void branch_scan_blocks(const DmcBufs &B)
+{
+    __shared__ long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < B.nblk; b0 += BR_THREADS) {
+        int b = b0 + threadIdx.x;
+        long long v = (b < B.nblk) ? __ldcg(B.blocksum + b) : 0;
+        long long tot;
+        long long ex = block_excl_scan(v, &tot);
+        long long carry = carry_s;
+        if (b < B.nblk) B.blockoff[b] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        DmcCtl *ctl = B.ctl;
+        long long total = carry_s;
+        ctl->total_children = total;
+        if (total > B.cap) { ctl->capacity_hits += 1; total = B.cap; }
+        ctl->W = (int) total;
+    }
+}
+
+// True in exactly one CTA of the grid: the last one to get here.  Its reads
+// (through __ldcg) see everything the other CTAs wrote before their call.
+__device__ __forceinline__ bool last_cta_done(unsigned int *counter)
+{
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int n = atomicAdd(counter, 1u);
+        is_last = (n == gridDim.x - 1);
+        if (is_last) *counter = 0;          // ready for the next step
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last;
+}
+
+// K4a+b: clone counts c_s = int(w_s + u_s) (qmc_base/dmc.py:641-643) and, in
+// the last CTA to finish, the scan of the per-CTA sums.
 __global__ void __launch_bounds__(BR_THREADS)
 branch_count_kernel(DmcBufs B, DmcConsts C)
 {
@@ -237,40 +283,49 @@ branch_count_kernel(DmcBufs B, DmcConsts C)
     long long tot;
     block_excl_scan(local, &tot);
     if (threadIdx.x == 0) B.blocksum[blockIdx.x] = tot;
+    if (last_cta_done(&B.ctl->done_count)) branch_scan_blocks(B);
 }
 
-// K4b: scan of the per-CTA sums; fixes W for this step.
-__global__ void __launch_bounds__(BR_THREADS)
-branch_scan_kernel(DmcBufs B)
+// K7: population control (qmc_base/dmc.py:758-771) from the (global) sums in
+// ctl->red, the per-step log, and the hand-over to the next step.  Runs
+// BEFORE the step kernel of the same time step, which therefore reads the
+// step index as ctl->step - 1.
+__device__ __forceinline__ void dmc_finalize(const DmcBufs &B,
+                                             const DmcConsts &C,
+                                             const DmcLog &L)
 {
-    __shared__ long long carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int b0 = 0; b0 < B.nblk; b0 += BR_THREADS) {
-        int b = b0 + threadIdx.x;
-        long long v = (b < B.nblk) ? B.blocksum[b] : 0;
-        long long tot;
-        long long ex = block_excl_scan(v, &tot);
-        long long carry = carry_s;
-        if (b < B.nblk) B.blockoff[b] = carry + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + tot;
-        __syncthreads();
+    DmcCtl *ctl = B.ctl;
+    double sE = ctl->red[0], sW = ctl->red[1];
+    ctl->tot_e += sE;
+    ctl->tot_w += sW;
+    double accum = ctl->tot_e / ctl->tot_w;
+    double eref = accum - C.nwc_over_dt * log(sW / C.target);
+    long long t = ctl->step;
+    ctl->eref[(t + 1) & 1] = eref;
+    ctl->last_energy = sE;
+    ctl->last_weight = sW;
+    ctl->last_accum = accum;
+    ctl->W_global = sW;
+    long long i = t - L.block_step0;
+    if (L.energy) {
+        L.energy[i] = sE;
+        L.weight[i] = sW;
+        L.num_walkers[i] = (unsigned long long) (sW + 0.5);
+        L.ref_energy[i] = eref;
+        L.accum_energy[i] = accum;
     }
-    if (threadIdx.x == 0) {
-        DmcCtl *ctl = B.ctl;
-        long long total = carry_s;
-        ctl->total_children = total;
-        if (total > B.cap) { ctl->capacity_hits += 1; total = B.cap; }
-        ctl->W = (int) total;
-    }
+    ctl->W_prev = ctl->W;
+    ctl->step = t + 1;
 }
 
-// K4c: children occupy consecutive slots in parent order, truncated at the
-// capacity (qmc_base/dmc.py:644-653); per-CTA partial of sum E over the
-// cloned parents (= state_energy, qmc_base/dmc.py:759-760).
+// K4c (+K7): children occupy consecutive slots in parent order, truncated at
+// the capacity (qmc_base/dmc.py:644-653); per-CTA partial of sum E over the
+// cloned parents (= state_energy, qmc_base/dmc.py:759-760).  The last CTA to
+// finish adds the partials in a fixed order into ctl->red and, on a single
+// rank (finalize != 0), runs the population control; with several ranks the
+// host all-reduces ctl->red first and then launches dmc_finalize_kernel.
 __global__ void __launch_bounds__(BR_THREADS)
-branch_fill_kernel(DmcBufs B)
+branch_fill_kernel(DmcBufs B, DmcConsts C, DmcLog L, int finalize)
 {
     const DmcCtl *ctl = B.ctl;
     const int par = (int) (ctl->step & 1);
@@ -308,15 +363,11 @@ branch_fill_kernel(DmcBufs B)
         __syncthreads();
     }
     if (threadIdx.x == 0) B.epart[blockIdx.x] = red[0];
-}
-
-// K7a: local {sum E_parents, W} into ctl->red (fixed order).
-__global__ void __launch_bounds__(BR_THREADS)
-dmc_local_sum_kernel(DmcBufs B)
-{
-    __shared__ double red[BR_THREADS];
+    if (!last_cta_done(&B.ctl->done_fill)) return;
     double acc = 0.0;
-    for (int b = threadIdx.x; b < B.nblk; b += BR_THREADS) acc += B.epart[b];
+    for (int b = threadIdx.x; b < B.nblk; b += BR_THREADS)
+        acc += __ldcg(B.epart + b);
+    __syncthreads();
     red[threadIdx.x] = acc;
     __syncthreads();
     for (int d = BR_THREADS / 2; d > 0; d >>= 1) {
@@ -326,36 +377,15 @@ dmc_local_sum_kernel(DmcBufs B)
     if (threadIdx.x == 0) {
         B.ctl->red[0] = red[0];
         B.ctl->red[1] = (double) B.ctl->W;
+        if (finalize) dmc_finalize(B, C, L);
     }
 }
 
-// K7b: population control (qmc_base/dmc.py:758-771) from the (global) sums in
-// ctl->red, the per-step log, and the hand-over to the next step.
+// K7 on several ranks: after the all-reduce of ctl->red.
 __global__ void dmc_finalize_kernel(DmcBufs B, DmcConsts C, DmcLog L)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    DmcCtl *ctl = B.ctl;
-    double sE = ctl->red[0], sW = ctl->red[1];
-    ctl->tot_e += sE;
-    ctl->tot_w += sW;
-    double accum = ctl->tot_e / ctl->tot_w;
-    double eref = accum - C.nwc_over_dt * log(sW / C.target);
-    long long t = ctl->step;
-    ctl->eref[(t + 1) & 1] = eref;
-    ctl->last_energy = sE;
-    ctl->last_weight = sW;
-    ctl->last_accum = accum;
-    ctl->W_global = sW;
-    long long i = t - L.block_step0;
-    if (L.energy) {
-        L.energy[i] = sE;
-        L.weight[i] = sW;
-        L.num_walkers[i] = (unsigned long long) (sW + 0.5);
-        L.ref_energy[i] = eref;
-        L.accum_energy[i] = accum;
-    }
-    ctl->W_prev = ctl->W;
-    ctl->step = t + 1;
+    dmc_finalize(B, C, L);
 }
 
 // ---------------------------------------------------------------------------
@@ -379,7 +409,7 @@ dmc_step_kernel(const __grid_constant__ DevModel M, GroupGeom geom, DmcBufs B,
     const int W = ctl->W;
     const long long s0 = (long long) blockIdx.x * geom.G;
     if (s0 >= W) return;
-    const long long t = ctl->step;
+    const long long t = ctl->step - 1;      // population control ran first
     const int par = (int) (t & 1);
     const double eref = ctl->eref[par];
     const double *pconfs = B.confs[par];
