@@ -518,8 +518,17 @@ int launch_density_step(qmcb_handle *h, long long step_idx)
     double *total = h->den_total + (size_t) pbuf * NB;
     if (!pure || step_idx < pfw) {
         const double *confs = B.confs[(int) ((h->step_host + step_idx) & 1)];
-        density_hist_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(
-            confs, B.ref, W_dev, N, NB, h->M.L / NB, hist, total, h->den_hi);
+        const size_t sm_bytes = (size_t) NB * sizeof(unsigned int);
+        const int use_smem = sm_bytes <= 160 * 1024;
+        if (use_smem && sm_bytes > 48 * 1024)
+            CUDA_TRY(h, cudaFuncSetAttribute(
+                            density_hist_kernel,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int) sm_bytes));
+        density_hist_kernel<<<h->sm_count * (use_smem ? 2 : 8), 256,
+                              use_smem ? sm_bytes : 0, h->stream>>>(
+            confs, B.ref, W_dev, N, NB, h->M.L / NB, hist, total, h->den_hi,
+            use_smem);
     }
     // sum over live slots = running total - rows of slots that died
     RowRange rr{};

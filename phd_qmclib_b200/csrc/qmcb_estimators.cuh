@@ -31,7 +31,7 @@ struct SsfArgs {
 
 // Thread (g, j): walker g of the CTA, modes [16 j, 16 j + 16).  For every
 // particle the phase e^{i k_m z} is seeded exactly at the first mode of the
-// chunk and advanced by the particle's unit rotation e^{i 2 pi z / L}.
+// chunk and advanced by a three-term recurrence in cos(2 pi z / L).
 __global__ void __launch_bounds__(SSF_THREADS)
 ssf_eval_kernel(SsfArgs a, int G, int nchunk)
 {
@@ -66,16 +66,22 @@ ssf_eval_kernel(SsfArgs a, int G, int nchunk)
             const double *px = sx + g * N, *pc = sc1 + g * N,
                          *ps = ss1 + g * N;
             for (int i = 0; i < N; ++i) {
-                double c, sn;
-                sincospi((double) m0 * px[i], &sn, &c);
-                const double c1 = pc[i], s1 = ps[i];
+                // three-term recurrence e^{i(m+1)t} = 2 cos t e^{imt}
+                // - e^{i(m-1)t}, seeded exactly at m0: one DFMA per
+                // component and mode; a rounding error is amplified by at
+                // most the distance to the seed (<= 16)
+                double cm, sm;
+                sincospi((double) m0 * px[i], &sm, &cm);
+                const double c1 = pc[i], s1 = ps[i], twoc = 2.0 * c1;
+                double cp = fma(cm, c1, sm * s1);       // mode m0 - 1
+                double sp = fma(sm, c1, -(cm * s1));
 #pragma unroll
                 for (int q = 0; q < SSF_CHUNK; ++q) {
-                    re[q] += c;
-                    im[q] += sn;
-                    double cn = fma(c, c1, -(sn * s1));
-                    sn = fma(sn, c1, c * s1);
-                    c = cn;
+                    re[q] += cm;
+                    im[q] += sm;
+                    double cn = fma(twoc, cm, -cp);
+                    double sn = fma(twoc, sm, -sp);
+                    cp = cm; sp = sm; cm = cn; sm = sn;
                 }
             }
             double *o = a.out + (s * a.M + m0) * 3;
@@ -171,14 +177,22 @@ __device__ __forceinline__ int py_floordiv_bin(double z, double b)
 // what lets the per-step sum over live slots be formed as
 //   total - (rows of dead slots that were live earlier in the block).
 // Counts are small integers held in doubles: the atomics are exact, hence
-// order-independent.  hi_dev tracks the highest slot count seen.
+// order-independent.  The counts for `total` are first gathered per CTA in
+// shared memory (32-bit atomics) so that the global array sees one atomic per
+// touched bin and CTA.  hi_dev tracks the highest slot count seen.
 __global__ void __launch_bounds__(256)
 density_hist_kernel(const double *confs, const int *ref, const int *W_dev,
                     int N, int nbins, double bin_size, double *hist,
-                    double *total, int *hi_dev)
+                    double *total, int *hi_dev, int use_smem)
 {
+    extern __shared__ unsigned int dens_smem[];
     const long long W = *W_dev;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(hi_dev, (int) W);
+    if (use_smem) {
+        for (int b = threadIdx.x; b < nbins; b += blockDim.x)
+            dens_smem[b] = 0u;
+        __syncthreads();
+    }
     const long long n = W * N;
     for (long long e = blockIdx.x * (long long) blockDim.x + threadIdx.x;
          e < n; e += (long long) gridDim.x * blockDim.x) {
@@ -188,7 +202,15 @@ density_hist_kernel(const double *confs, const int *ref, const int *W_dev,
         int b = py_floordiv_bin(z, bin_size);
         b = b < 0 ? 0 : (b >= nbins ? nbins - 1 : b);     // quirk Q5: clamp
         atomicAdd(hist + s * nbins + b, 1.0);
-        atomicAdd(total + b, 1.0);
+        if (use_smem) atomicAdd(dens_smem + b, 1u);
+        else atomicAdd(total + b, 1.0);
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
+            unsigned int c = dens_smem[b];
+            if (c) atomicAdd(total + b, (double) c);
+        }
     }
 }
 
