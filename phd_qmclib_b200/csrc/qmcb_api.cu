@@ -1403,8 +1403,7 @@ int qmcb_vmc_init(qmcb_handle *h, const qmcb_vmc_params *params,
                                   "(gaussian)");
     CUDA_TRY(h, cudaSetDevice(h->device));
     const int N = h->M.nop, M = params->ssf_num_modes;
-    size_t vsm = (size_t) h->geom.smem_bytes + 8
-                 + (size_t) h->geom.G * h->M.nb * VMC_MB * sizeof(double2);
+    size_t vsm = (size_t) h->geom.smem_bytes;
     if (vsm > (size_t) h->max_smem)
         FAIL(h, QMCB_ERR_INVALID, "boson_number too large for the VMC kernel");
     CUDA_TRY(h, cudaFuncSetAttribute(
@@ -1485,8 +1484,7 @@ int qmcb_vmc_run_block(qmcb_handle *h, int64_t ns, double *lnpsi,
         CUDA_TRY(h, cudaMemsetAsync(h->vmc_sum_ssf, 0,
                                     C * M * 3 * sizeof(double), h->stream));
     const GroupGeom &g = h->geom;
-    size_t vsm = (size_t) g.smem_bytes + 8
-                 + (size_t) g.G * h->M.nb * VMC_MB * sizeof(double2);
+    size_t vsm = (size_t) g.smem_bytes;
     long long ctas = ((long long) C + g.G - 1) / g.G;
     int grid = (int) std::min<long long>(ctas, (long long) h->sm_count * 64);
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));

@@ -45,10 +45,6 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
 {
     GroupSmem sm = group_smem(geom);
     GroupIdx x = group_index(M, geom);
-    extern __shared__ __align__(16) double qmcb_smem[];
-    // S(k) partials live behind the pair tables: [G][nb][VMC_MB] double2
-    double2 *part_all = reinterpret_cast<double2 *>(
-        qmcb_smem + ((geom.G * (geom.tab_stride + geom.q_stride) + 1) & ~1));
     const int N = M.nop, nb = M.nb;
     const bool vec_ok = (N % 2) == 0;
     const int nvalid = min(TB, N - TB * x.I);
@@ -66,7 +62,9 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
             e_prev = S.eprev[c];
         }
         const uint32_t gc = (uint32_t) (a.chain_offset + c);
-        double2 *part = part_all + (size_t) x.g * nb * VMC_MB;
+        // S(k) partials [nb][VMC_MB] reuse the walker's pair tables, which
+        // are dead between two evaluations (8 * nb <= 20 * nbp double2)
+        double2 *part = reinterpret_cast<double2 *>(sm.tab(x.g));
         for (long long st = 0; st < a.ns; ++st) {
             const bool ini = a.first && st == 0;
             const long long gs = a.gstep0 + st - (a.first ? 1 : 0);
