@@ -1227,6 +1227,32 @@ int qmcb_comm_init(qmcb_handle *h, const uint8_t *id, int32_t world_size,
     h->world = world_size;
     h->rank = rank;
     CUDA_TRY(h, cudaMalloc(&h->d_counts, world_size * sizeof(long long)));
+    // NCCL sets its peer-to-peer channels up lazily, on the first send/recv
+    // of every (source, destination) pair, and that costs tens of
+    // milliseconds per pair.  The rebalance may pair any two ranks, so open
+    // all channels (and the all-reduce / all-gather rings) now rather than
+    // inside a sampling block.
+    CUDA_TRY(h, cudaMemsetAsync(h->d_counts, 0,
+                                world_size * sizeof(long long), h->stream));
+    long long *d_tmp = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d_tmp, 2 * world_size * sizeof(long long)));
+    CUDA_TRY(h, cudaMemsetAsync(d_tmp, 0, 2 * world_size * sizeof(long long),
+                                h->stream));
+    NCCL_TRY(h, api->GroupStart());
+    for (int p = 0; p < world_size; ++p) {
+        if (p == rank) continue;
+        NCCL_TRY(h, api->Send(h->d_counts + rank, 1, ncclInt64, p, h->comm,
+                              h->stream));
+        NCCL_TRY(h, api->Recv(d_tmp + p, 1, ncclInt64, p, h->comm,
+                              h->stream));
+    }
+    NCCL_TRY(h, api->GroupEnd());
+    NCCL_TRY(h, api->AllReduce(d_tmp + world_size, d_tmp + world_size, 2,
+                               ncclDouble, ncclSum, h->comm, h->stream));
+    NCCL_TRY(h, api->AllGather(h->d_counts + rank, h->d_counts, 1, ncclInt64,
+                               h->comm, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaFree(d_tmp));
     return QMCB_OK;
 }
 
