@@ -219,29 +219,48 @@ __device__ __forceinline__ OneBody one_body(const DevModel &M, double z)
     OneBody o;
     double n_cell = floor(z);
     double zc = z - n_cell;                         // z mod 1, exact
-    if (M.za < zc) {                                // barrier
+    const bool barrier = M.za < zc;
+    if (!LN) {
+        // Branch-free: both regions are evaluated and one is selected, so
+        // that the four particles of a thread interleave instead of taking
+        // divergent branches one after the other.  tanh from one exp and one
+        // reciprocal: absolute error ~1e-16, which is what matters for a
+        // term added to O(1) drifts and energies.
+        double argb = M.kp1 * (zc - 1.0 + 0.5 * M.zb);
+        double ex = exp(-2.0 * fabs(argb));
+        double th = copysign((1.0 - ex) * fast_rcp(1.0 + ex), argb);
+        double ldz_b = M.kp1 * th;
+        double s, c;
+        sincospi(M.k1_over_pi * (zc - 0.5 * M.za), &s, &c);
+        double ldz_w = -M.k1 * (s * fast_rcp(c));
+        o.ldz = barrier ? ldz_b : ldz_w;
+        o.kin = fma(o.ldz, o.ldz, barrier ? -(M.v0 - M.e0) : M.e0);
+        // mrbp_qmc/model.py:533-551: every defects_sep-th cell is a defect
+        double vb = M.vdef;
+        if (M.defects_sep != 1
+            && fmod(n_cell, (double) M.defects_sep) != 0.0)
+            vb = M.v0;
+        o.pot = barrier ? vb : 0.0;
+        o.lnf = 0.0;
+        return o;
+    }
+    if (barrier) {
         double arg = M.kp1 * (zc - 1.0 + 0.5 * M.zb);
-#ifndef QMCB_LIBM_TANH
-        // tanh from one exp and one reciprocal: absolute error ~1e-16, which
-        // is what matters for a term added to O(1) drifts and energies
         double ex = exp(-2.0 * fabs(arg));
         double th = copysign((1.0 - ex) * fast_rcp(1.0 + ex), arg);
-#else
-        double th = tanh(arg);
-#endif
         o.ldz = M.kp1 * th;
         o.kin = -(M.v0 - M.e0) + o.ldz * o.ldz;
         bool defect = (M.defects_sep == 1)
                       || (fmod(n_cell, (double) M.defects_sep) == 0.0);
         o.pot = defect ? M.vdef : M.v0;
-        if (LN) o.lnf = log(cosh(arg));
+        o.lnf = log(cosh(arg));
     } else {                                        // well
         double s, c;
         sincospi(M.k1_over_pi * (zc - 0.5 * M.za), &s, &c);
         o.ldz = -M.k1 * (s * fast_rcp(c));
         o.kin = M.e0 + o.ldz * o.ldz;
         o.pot = 0.0;
-        if (LN) o.lnf = M.ln_cf + log(fabs(c));
+        o.lnf = M.ln_cf + log(fabs(c));
     }
     return o;
 }

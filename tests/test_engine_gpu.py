@@ -240,3 +240,65 @@ def test_vmc_blocks_vs_oracle(eng_mod, oracle, name, nch, ns, modes, spread,
     assert np.allclose(confs[:, 0], cur[:, 0], rtol=0, atol=1e-12)
     assert rel_err(lnpsi, ln) < 1e-11
     eng.close()
+
+
+@pytest.mark.parametrize('kwargs', [
+    # every cell is a defect (defects_sep == 1 with V_defect != V0)
+    dict(lattice_depth=40.0, lattice_ratio=1, interaction_strength=2,
+         boson_number=10, supercell_size=10, tbf_contact_cutoff=2.5,
+         num_defects=10, defect_magnitude=15.0),
+    # r_m = L/2: every pair is on the short-range branch
+    dict(lattice_depth=20.0, lattice_ratio=0.5, interaction_strength=3,
+         boson_number=12, supercell_size=9, tbf_contact_cutoff=4.5),
+    # very weak interaction: k2 tiny, large unit-conversion factors
+    dict(lattice_depth=10.0, lattice_ratio=1, interaction_strength=1e-6,
+         boson_number=9, supercell_size=9, tbf_contact_cutoff=2.0),
+    # free gas (no lattice) and a single particle block
+    dict(lattice_depth=0.0, lattice_ratio=1, interaction_strength=5,
+         boson_number=3, supercell_size=4, tbf_contact_cutoff=1.0),
+])
+def test_model_eval_edge_specs_vs_oracle(eng_mod, oracle, kwargs):
+    from phd_qmclib_b200 import model
+    spec = model.Spec(**kwargs)
+    p = model.param_block(spec)
+    nop, size = spec.boson_number, spec.supercell_size
+    rng = np.random.default_rng(17)
+    confs = np.zeros((400, 2, nop))
+    confs[:, 0] = rng.random((400, nop)) * size
+    confs[0, 0] = np.linspace(0, size, nop, endpoint=False)
+    ref = oracle.model_eval(p, confs)
+    with eng_mod.Engine(spec) as eng:
+        o = eng.model_eval(confs)
+    assert scaled_err(o['lnpsi'], ref['lnpsi']) < TOL
+    assert scaled_err(o['energy'], ref['energy']) < TOL
+    assert maxnorm_err(o['drift'], ref['drift']) < TOL
+
+
+def test_dmc_restart_is_bit_exact(eng_mod):
+    """qmcb_dmc_get_next -> qmcb_dmc_set_state on a fresh handle continues the
+    run bit for bit (what a checkpoint/resume of the evolved population
+    needs: walkers, weights, the per-slot stale energies of quirk Q1, the
+    running totals and the step counter that keys the RNG)."""
+    g = golden('model_lat_n50.npz')
+    p = g['params']
+    spec = (p[:12], p[12:19], p[19:])
+    rng = np.random.default_rng(8)
+    ini = np.zeros((60, 2, 50))
+    ini[:, 0] = rng.random((60, 50)) * 50
+    a = eng_mod.Engine(spec)
+    dp = a.dmc_params(1e-3, 96, 60, 0.25, 13, 0.0, 50.0)
+    a.dmc_init(dp, ini)
+    a.dmc_run_block(7)
+    nx = a.dmc_get_next()
+    want = a.dmc_run_block(9)
+    b = eng_mod.Engine(spec)
+    b.dmc_set_state(dp, nx['confs'], nx['energy'], nx['weight'],
+                    nx['scalars'], slot_energy=nx['slot_energy'])
+    got = b.dmc_run_block(9)
+    for k in want:
+        assert np.array_equal(want[k], got[k]), k
+    sa, sb = a.dmc_get_state(), b.dmc_get_state()
+    for k in ('confs', 'energy', 'weight', 'mask', 'cloning_ref'):
+        assert np.array_equal(sa[k], sb[k]), k
+    a.close()
+    b.close()
