@@ -81,11 +81,19 @@ def gen_model(mrbp, name, kwargs, rng):
     fdk = np.array([[cf.fourier_density(k, c, *cfc) for k in momenta]
                     for c in confs])
     ssf = np.stack([(fdk * fdk.conj()).real, fdk.real, fdk.imag], axis=-1)
+    # one-body density matrix at a few displacements, incl. beyond the box
+    size = spec.supercell_size
+    obd_offsets = np.array([0., 0.05, 0.37, 1.0, 2.5, 0.5 * size, -0.3,
+                            -1.7 * size])
+    nobd = min(len(confs), 4)
+    obd = np.array([[cf.one_body_density(sz, c, *cfc) for sz in obd_offsets]
+                    for c in confs[:nobd]])
     out = dict(spec_keys=np.array(list(kwargs.keys())),
                spec_vals=np.array([float(v) for v in kwargs.values()]),
                params=param_block(spec), confs=confs, lnpsi=lnpsi,
                energy=energy, drift=drift, ith_energy=e_and_d[..., 0],
-               ssf=ssf, num_modes=num_modes)
+               ssf=ssf, num_modes=num_modes, obd_offsets=obd_offsets,
+               obd=obd)
     np.savez_compressed(os.path.join(GOLDEN, f'model_{name}.npz'), **out)
     print(f'model_{name}: lnpsi[0]={lnpsi[0]:.15g} E[0]={energy[0]:.15g}')
 

@@ -49,6 +49,9 @@ def lib():
     L.qmco_model_eval.restype = None
     L.qmco_fourier_density.argtypes = [_f64p, _f64p, C.c_int64, C.c_int, _f64p]
     L.qmco_fourier_density.restype = None
+    L.qmco_one_body_density.argtypes = [_f64p, _f64p, C.c_int64, _f64p,
+                                        C.c_int64, _f64p]
+    L.qmco_one_body_density.restype = None
     L.qmco_rng_uniform2.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32,
                                     C.c_uint32, C.c_uint32, _f64p]
     L.qmco_rng_normal2.argtypes = L.qmco_rng_uniform2.argtypes
@@ -133,6 +136,19 @@ def fourier_density(params, confs, num_modes):
         confs = confs[None]
     out = np.empty((confs.shape[0], num_modes, 3))
     lib().qmco_fourier_density(p, confs, confs.shape[0], num_modes, out)
+    return out
+
+
+def one_body_density(params, confs, offsets):
+    """confs [B,2,N], offsets [S] -> [B,S]."""
+    p = _params(params)
+    confs = np.ascontiguousarray(confs, dtype=np.float64)
+    if confs.ndim == 2:
+        confs = confs[None]
+    offsets = np.ascontiguousarray(offsets, dtype=np.float64)
+    out = np.empty((confs.shape[0], len(offsets)))
+    lib().qmco_one_body_density(p, confs, confs.shape[0], offsets,
+                                len(offsets), out)
     return out
 
 

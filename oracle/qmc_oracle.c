@@ -316,6 +316,46 @@ QMCO_API void qmco_fourier_density(const double *p, const double *confs,
     }
 }
 
+/* qmc_base/jastrow/model.py:859-965: local one-body density matrix,
+ * <Psi(z_i + sz) / Psi(z_i)> averaged over the particles.
+ * out: [nconf][nsz]. */
+static double ith_one_body_density(int i, double sz, const double *pos,
+                                   const double *p)
+{
+    int nop = (int) p[P_NOP];
+    double acc = 0.;
+    if (p[P_FREE] != 0. && p[P_IDEAL] != 0.) return acc;   /* as the reference */
+    double z_i = pos[i], z_s = z_i + sz;
+    if (p[P_FREE] == 0.)
+        acc += log(one_body_func(z_s, p)) - log(one_body_func(z_i, p));
+    if (p[P_IDEAL] == 0.) {
+        for (int j = 0; j < nop; ++j) {
+            if (j == i) continue;
+            double d0 = min_distance(z_i, pos[j], p[P_L]);
+            double d1 = min_distance(z_s, pos[j], p[P_L]);
+            acc += log(two_body_func(fabs(d1), p))
+                   - log(two_body_func(fabs(d0), p));
+        }
+    }
+    return exp(acc);
+}
+
+QMCO_API void qmco_one_body_density(const double *p, const double *confs,
+                                    int64_t nconf, const double *sz,
+                                    int64_t nsz, double *out)
+{
+    int nop = (int) p[P_NOP];
+#pragma omp parallel for schedule(static) collapse(2)
+    for (int64_t b = 0; b < nconf; ++b)
+        for (int64_t s = 0; s < nsz; ++s) {
+            const double *pos = confs + b * 2 * nop;
+            double obd = 0.;
+            for (int i = 0; i < nop; ++i)
+                obd += ith_one_body_density(i, sz[s], pos, p);
+            out[b * nsz + s] = obd / nop;
+        }
+}
+
 /* ------------------------------------------------------------------ */
 /* RNG convention (deviation D1), shared bit-for-bit with the engine   */
 /* (phd_qmclib_b200/csrc/qmcb_rng.cuh).                                */

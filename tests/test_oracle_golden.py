@@ -17,6 +17,10 @@ def test_model_eval(oracle, name):
     assert maxnorm_err(o['drift'], g['drift']) < TOL
     s = oracle.fourier_density(g['params'], g['confs'], int(g['num_modes']))
     assert np.max(np.abs(s - g['ssf'])) < 1e-12 * g['confs'].shape[2] ** 2
+    nobd = g['obd'].shape[0]
+    obd = oracle.one_body_density(g['params'], g['confs'][:nobd],
+                                  g['obd_offsets'])
+    assert rel_err(obd, g['obd']) < 1e-12
 
 
 @pytest.mark.parametrize('name', golden_names('dmc_step_'))
