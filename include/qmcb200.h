@@ -140,6 +140,53 @@ QMCB_API int qmcb_fourier_density(qmcb_handle *h, const double *confs,
                                   int64_t nconf, int32_t num_modes,
                                   double *out);
 
+/* Replaces core_funcs.one_body_density (qmc_base/jastrow/model.py:934-965,
+ * per-particle term :859-931) and its broadcasting gufunc
+ * PhysicalFuncs.one_body_density (:1069-1091):
+ * out [nconf][num_offsets] = (1/N) sum_i Psi(z_i + offsets[s]) / Psi for each
+ * configuration.  Offsets may lie outside the box (the wave function is
+ * periodic in L). */
+QMCB_API int qmcb_one_body_density(qmcb_handle *h, const double *confs,
+                                   int64_t nconf, const double *offsets,
+                                   int32_t num_offsets, double *out);
+/* Same, all pointers in DEVICE memory; asynchronous on the engine's stream. */
+QMCB_API int qmcb_one_body_density_device(qmcb_handle *h,
+                                          const double *d_confs,
+                                          int64_t nconf,
+                                          const double *d_offsets,
+                                          int32_t num_offsets,
+                                          double *d_out);
+
+/* Replaces the gufunc PhysicalFuncs.fourier_density
+ * (qmc_base/jastrow/model.py:1093-1122) for an ARBITRARY momentum set:
+ * out [nconf][nk][2] = (Re, Im) of rho_k = sum_i exp(i kz z_i). */
+QMCB_API int qmcb_fourier_density_k(qmcb_handle *h, const double *confs,
+                                    int64_t nconf, const double *kz,
+                                    int32_t nk, double *out);
+
+/* ---- trial-wave-function optimisation (correlated sampling) ------------- */
+/* Swap the model scalars of a live handle (CSWFOptimizer.update_spec,
+ * mrbp_qmc/model.py:852-862, changes tbf_contact_cutoff and with it the six
+ * two-body scalars).  boson_number must not change. */
+QMCB_API int qmcb_set_model_params(qmcb_handle *h,
+                                   const qmcb_model_params *params);
+/* Keep the configuration set of the optimiser on the device
+ * (CSWFOptimizer.sys_conf_set / ini_wf_abs_log_set, mrbp_qmc/model.py:828-832):
+ * confs [nconf][2][N], ini_lnpsi [nconf] (NULL: evaluate it with the handle's
+ * current parameters). */
+QMCB_API int qmcb_cs_load(qmcb_handle *h, const double *confs, int64_t nconf,
+                          const double *ini_lnpsi);
+/* Replaces CSWFOptimizer.principal_function
+ * (qmc_base/jastrow/model.py:1186-1206): ln|Psi| and E_L of the loaded set
+ * under the `trial` scalars (NULL: the handle's own; wf_abs_log_and_energy_set,
+ * mrbp_qmc/model.py:889-903), weights exp(2 (ln|Psi| - ln|Psi_0|)), and the
+ * weighted variance of E_L (weighed_variance, :1147-1165), all on the device.
+ * ref_energy = the weighted mean energy; lnpsi/energy [nconf] host, any
+ * output may be NULL. */
+QMCB_API int qmcb_cs_variance(qmcb_handle *h, const qmcb_model_params *trial,
+                              double *variance, double *ref_energy,
+                              double *lnpsi, double *energy);
+
 /* ---- DMC ---------------------------------------------------------------- */
 /* Replaces Sampling.build_state (mrbp_qmc/dmc.py:268-328) +
  * prepare_state_data (qmc_base/jastrow/dmc.py:1030-1174) + the three-buffer

@@ -88,8 +88,14 @@ def gen_model(mrbp, name, kwargs, rng):
     nobd = min(len(confs), 4)
     obd = np.array([[cf.one_body_density(sz, c, *cfc) for sz in obd_offsets]
                     for c in confs[:nobd]])
+    # rho_k at momenta that are NOT multiples of 2 pi / L (the gufunc of
+    # PhysicalFuncs takes any kz_set)
+    kz_set = np.array([0.0, 0.3, 1.234, -2.5, 7.0, 2 * PI / size])
+    fdk_k = np.array([[cf.fourier_density(k, c, *cfc) for k in kz_set]
+                      for c in confs])
     out = dict(spec_keys=np.array(list(kwargs.keys())),
                spec_vals=np.array([float(v) for v in kwargs.values()]),
+               kz_set=kz_set, fdk_k=fdk_k,
                params=param_block(spec), confs=confs, lnpsi=lnpsi,
                energy=energy, drift=drift, ith_energy=e_and_d[..., 0],
                ssf=ssf, num_modes=num_modes, obd_offsets=obd_offsets,
@@ -363,16 +369,63 @@ def gen_dmc_stat(mrbp, name, kwargs, *, n_target, wmax, dt, nts, nblocks,
           f'{epn.std(ddof=1) / math.sqrt(len(epn)):.6f} (naive)')
 
 
+def gen_cswf(mrbp, name, kwargs, rng, *, nconf, cutoffs):
+    """Correlated-sampling objective of the wave-function optimiser
+    (mrbp_qmc/model.py:817-942) on a fixed configuration set: ln|Psi| and
+    E_L under each trial tbf_contact_cutoff from the reference's core
+    functions, the variance from the reference's own weighed_variance."""
+    import attr
+    from phd_qmclib.qmc_base import jastrow
+    model = mrbp.model
+    spec = model.Spec(**kwargs)
+    cf = model.core_funcs
+    # one particle per randomly chosen cell, jittered inside the well: the
+    # weights of such a set are comparable (iid uniform positions would
+    # leave a single configuration with all the weight)
+    nop, size = spec.boson_number, spec.supercell_size
+    confs = np.zeros((nconf, 2, nop))
+    for c in confs:
+        cells = np.sort(rng.choice(int(size), nop, replace=False))
+        c[0] = cells + spec.well_width * (0.5 + 0.5 * (rng.random(nop) - 0.5))
+    ini = np.array([cf.wf_abs_log(c, *spec.cfc_spec) for c in confs])
+    blocks, lns, ens, var = [], [], [], []
+    for rm in cutoffs:
+        trial = attr.evolve(spec, tbf_contact_cutoff=float(rm))
+        cfc = trial.cfc_spec
+        ln = np.array([cf.wf_abs_log(c, *cfc) for c in confs])
+        en = np.array([cf.energy(c, *cfc) for c in confs])
+        blocks.append(param_block(trial))
+        lns.append(ln)
+        ens.append(en)
+        var.append(jastrow.CSWFOptimizer.weighed_variance(2 * (ln - ini), en))
+    np.savez_compressed(
+        os.path.join(GOLDEN, f'cswf_{name}.npz'),
+        spec_keys=np.array(list(kwargs.keys())),
+        spec_vals=np.array([float(v) for v in kwargs.values()]),
+        params=param_block(spec), confs=confs, ini_lnpsi=ini,
+        cutoffs=np.array(cutoffs, dtype=float), trial_params=np.array(blocks),
+        lnpsi=np.array(lns), energy=np.array(ens), variance=np.array(var))
+    print(f'cswf_{name}: variance = {np.array(var)}')
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     which = set(sys.argv[1:]) or {'model', 'step', 'branch', 'blocks', 'vmc',
-                                  'stat'}
+                                  'stat', 'cswf'}
     mrbp = refshim.load()
     from phd_qmclib.mrbp_qmc import dmc, model, vmc  # noqa: F401
     draw_uniform, draw_dmc = numba_draws()
     if 'model' in which:
         for i, (name, kw) in enumerate(SPECS.items()):
             gen_model(mrbp, name, kw, np.random.default_rng(100 + i))
+    if 'cswf' in which:
+        gen_cswf(mrbp, 'll_n16', SPECS['ll_n16'], np.random.default_rng(600),
+                 nconf=96, cutoffs=[0.05, 1.0, 2.5, 4.0, 6.0, 7.92])
+        gen_cswf(mrbp, 'lat_n50', SPECS['lat_n50'],
+                 np.random.default_rng(601), nconf=64,
+                 cutoffs=[0.05, 3.0, 12.5, 20.0, 24.75])
+        gen_cswf(mrbp, 'odd_n7', SPECS['odd_n7'], np.random.default_rng(602),
+                 nconf=1500, cutoffs=[0.4, 3.3, 4.9])
     if 'step' in which:
         for i, name in enumerate(['ll_n16', 'lat_n50', 'defects_n20',
                                   'odd_n7']):

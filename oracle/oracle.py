@@ -49,6 +49,9 @@ def lib():
     L.qmco_model_eval.restype = None
     L.qmco_fourier_density.argtypes = [_f64p, _f64p, C.c_int64, C.c_int, _f64p]
     L.qmco_fourier_density.restype = None
+    L.qmco_fourier_density_k.argtypes = [_f64p, _f64p, C.c_int64, _f64p,
+                                         C.c_int64, _f64p]
+    L.qmco_fourier_density_k.restype = None
     L.qmco_one_body_density.argtypes = [_f64p, _f64p, C.c_int64, _f64p,
                                         C.c_int64, _f64p]
     L.qmco_one_body_density.restype = None
@@ -137,6 +140,31 @@ def fourier_density(params, confs, num_modes):
     out = np.empty((confs.shape[0], num_modes, 3))
     lib().qmco_fourier_density(p, confs, confs.shape[0], num_modes, out)
     return out
+
+
+def fourier_density_k(params, confs, kz_set):
+    """confs [B,2,N], kz_set [K] -> complex [B,K]."""
+    p = _params(params)
+    confs = np.ascontiguousarray(confs, dtype=np.float64)
+    if confs.ndim == 2:
+        confs = confs[None]
+    kz = np.ascontiguousarray(kz_set, dtype=np.float64)
+    out = np.empty((confs.shape[0], len(kz), 2))
+    lib().qmco_fourier_density_k(p, confs, confs.shape[0], kz, len(kz), out)
+    return out[..., 0] + 1j * out[..., 1]
+
+
+def weighed_variance(wf_abs_log_set, ini_wf_abs_log_set, energy_set):
+    """Correlated-sampling objective: qmc_base/jastrow/model.py:1147-1165
+    with the weights of principal_function (:1199-1203).  Returns
+    (variance, weighted mean energy)."""
+    wl = 2 * (np.asarray(wf_abs_log_set) - np.asarray(ini_wf_abs_log_set))
+    energy_set = np.asarray(energy_set)
+    rel_weights = np.exp(wl - wl.max())
+    weight_sum = rel_weights.sum()
+    ref_energy = (rel_weights * energy_set).sum() / weight_sum
+    e_diff = rel_weights * (energy_set - ref_energy) ** 2
+    return e_diff.sum() / weight_sum, ref_energy
 
 
 def one_body_density(params, confs, offsets):

@@ -316,6 +316,23 @@ QMCO_API void qmco_fourier_density(const double *p, const double *confs,
     }
 }
 
+/* The gufunc PhysicalFuncs.fourier_density
+ * (qmc_base/jastrow/model.py:1093-1122): arbitrary momenta kz[nk];
+ * out: [nconf][nk][2] = (Re, Im). */
+QMCO_API void qmco_fourier_density_k(const double *p, const double *confs,
+                                     int64_t nconf, const double *kz,
+                                     int64_t nk, double *out)
+{
+    int nop = (int) p[P_NOP];
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < nconf; ++b) {
+        const double *pos = confs + b * 2 * nop;
+        for (int64_t m = 0; m < nk; ++m)
+            fourier_density(kz[m], pos, nop, out + (b * nk + m) * 2,
+                            out + (b * nk + m) * 2 + 1);
+    }
+}
+
 /* qmc_base/jastrow/model.py:859-965: local one-body density matrix,
  * <Psi(z_i + sz) / Psi(z_i)> averaged over the particles.
  * out: [nconf][nsz]. */

@@ -22,6 +22,9 @@ SYMBOLS = [
     'qmcb_dmc_rebalance', 'qmcb_vmc_init', 'qmcb_vmc_run_block',
     'qmcb_vmc_get_state', 'qmcb_measure_fp64_sustained', 'qmcb_stream',
     'qmcb_host_alloc', 'qmcb_host_free', 'qmcb_rebalance_plan',
+    'qmcb_one_body_density', 'qmcb_one_body_density_device',
+    'qmcb_fourier_density_k', 'qmcb_set_model_params', 'qmcb_cs_load',
+    'qmcb_cs_variance',
 ]
 
 
@@ -88,6 +91,13 @@ def load():
     L.qmcb_model_eval.argtypes = [vp, vp, i64, vp, vp, vp]
     L.qmcb_model_eval_device.argtypes = [vp, vp, i64, vp, vp, vp]
     L.qmcb_fourier_density.argtypes = [vp, vp, i64, i32, vp]
+    L.qmcb_one_body_density.argtypes = [vp, vp, i64, vp, i32, vp]
+    L.qmcb_one_body_density_device.argtypes = [vp, vp, i64, vp, i32, vp]
+    L.qmcb_fourier_density_k.argtypes = [vp, vp, i64, vp, i32, vp]
+    L.qmcb_set_model_params.argtypes = [vp, C.POINTER(ModelParams)]
+    L.qmcb_cs_load.argtypes = [vp, vp, i64, vp]
+    L.qmcb_cs_variance.argtypes = [vp, C.POINTER(ModelParams),
+                                   C.POINTER(dbl), C.POINTER(dbl), vp, vp]
     L.qmcb_dmc_init.argtypes = [vp, C.POINTER(DMCParams), vp, i64, dbl, i64]
     L.qmcb_dmc_set_state.argtypes = [vp, C.POINTER(DMCParams), vp, vp, vp,
                                      vp, C.POINTER(StateScalars), i64]

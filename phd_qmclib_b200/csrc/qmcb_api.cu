@@ -120,6 +120,12 @@ struct qmcb_handle {
     int *den_hi = nullptr;                      // highest slot count seen
     long long est_log_cap = 0;
 
+    // correlated-sampling set of the wave-function optimiser (device)
+    double *cs_confs = nullptr;         // [cs_n][2][N]
+    double *cs_ln0 = nullptr;           // [cs_n] ln|Psi| the set was drawn from
+    double *cs_work = nullptr;          // [2 cs_n + 4]: ln|Psi|, E_L, results
+    long long cs_n = 0;
+
     // VMC
     bool vmc_ready = false;
     qmcb_vmc_params vp{};
@@ -665,6 +671,7 @@ void qmcb_destroy(qmcb_handle *h)
     free_vmc(h);
     cudaFree(h->d_scratch);
     cudaFree(h->d_counts);
+    cudaFree(h->cs_confs); cudaFree(h->cs_ln0); cudaFree(h->cs_work);
     if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
     for (auto ev : h->step_ev) cudaEventDestroy(ev);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -752,6 +759,202 @@ int qmcb_fourier_density(qmcb_handle *h, const double *confs, int64_t nconf,
     CUDA_TRY(h, cudaMemcpyAsync(out, d_out, no * sizeof(double),
                                 cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return QMCB_OK;
+}
+
+int qmcb_one_body_density_device(qmcb_handle *h, const double *d_confs,
+                                 int64_t nconf, const double *d_offsets,
+                                 int32_t num_offsets, double *d_out)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (nconf < 0 || num_offsets < 0
+        || (nconf > 0 && num_offsets > 0
+            && (!d_confs || !d_offsets || !d_out)))
+        FAIL(h, QMCB_ERR_INVALID, "bad arguments");
+    if (nconf == 0 || num_offsets == 0) return QMCB_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int N = h->M.nop, S = num_offsets;
+    // items (configuration, offset) are dealt to CTAs in order; a CTA needs
+    // the tables of every configuration its items touch
+    int nt = 128;
+    size_t smem = 0;
+    for (; nt >= 32; nt /= 2) {
+        int gmax = (nt - 1) / S + 2;
+        if ((long long) gmax > nconf) gmax = (int) nconf;
+        smem = (size_t) gmax * obd_slot_doubles(N) * sizeof(double);
+        if (smem <= (size_t) h->max_smem) break;
+    }
+    if (nt < 32)
+        FAIL(h, QMCB_ERR_INVALID,
+             "boson_number too large for the one-body density tables");
+    if (smem > 48 * 1024)
+        CUDA_TRY(h, cudaFuncSetAttribute(
+                        obd_kernel,
+                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        (int) smem));
+    ObdArgs a{};
+    a.confs = d_confs; a.nconf = nconf; a.offsets = d_offsets; a.S = S;
+    a.out = d_out;
+    long long items = (long long) nconf * S;
+    long long grid = (items + nt - 1) / nt;
+    if (grid > 0x7fffffffll)
+        FAIL(h, QMCB_ERR_INVALID, "too many (configuration, offset) items");
+    obd_kernel<<<(unsigned) grid, nt, smem, h->stream>>>(h->M, a);
+    CUDA_TRY(h, cudaGetLastError());
+    return QMCB_OK;
+}
+
+int qmcb_one_body_density(qmcb_handle *h, const double *confs, int64_t nconf,
+                          const double *offsets, int32_t num_offsets,
+                          double *out)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (nconf < 0 || num_offsets < 0
+        || (nconf > 0 && num_offsets > 0 && (!confs || !offsets || !out)))
+        FAIL(h, QMCB_ERR_INVALID, "bad arguments");
+    if (nconf == 0 || num_offsets == 0) return QMCB_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int N = h->M.nop;
+    size_t nc = (size_t) nconf * 2 * N, no = (size_t) nconf * num_offsets;
+    int rc = ensure_scratch(h, (nc + no + num_offsets) * sizeof(double));
+    if (rc) return rc;
+    double *d_confs = h->d_scratch, *d_out = d_confs + nc, *d_off = d_out + no;
+    CUDA_TRY(h, cudaMemcpyAsync(d_confs, confs, nc * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_off, offsets, num_offsets * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+    rc = qmcb_one_body_density_device(h, d_confs, nconf, d_off, num_offsets,
+                                      d_out);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(out, d_out, no * sizeof(double),
+                                cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return QMCB_OK;
+}
+
+int qmcb_fourier_density_k(qmcb_handle *h, const double *confs,
+                           int64_t nconf, const double *kz, int32_t nk,
+                           double *out)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (nconf < 0 || nk < 0
+        || (nconf > 0 && nk > 0 && (!confs || !kz || !out)))
+        FAIL(h, QMCB_ERR_INVALID, "bad arguments");
+    if (nconf == 0 || nk == 0) return QMCB_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int N = h->M.nop;
+    size_t nc = (size_t) nconf * 2 * N, no = (size_t) nconf * nk * 2;
+    int rc = ensure_scratch(h, (nc + no + nk) * sizeof(double));
+    if (rc) return rc;
+    double *d_confs = h->d_scratch, *d_out = d_confs + nc, *d_k = d_out + no;
+    CUDA_TRY(h, cudaMemcpyAsync(d_confs, confs, nc * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_k, kz, nk * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+    long long items = (long long) nconf * nk;
+    int grid = (int) std::min<long long>((items + 127) / 128,
+                                         (long long) h->sm_count * 32);
+    fdk_general_kernel<<<grid, 128, 0, h->stream>>>(d_confs, nconf, N, d_k,
+                                                    nk, d_out);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemcpyAsync(out, d_out, no * sizeof(double),
+                                cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return QMCB_OK;
+}
+
+int qmcb_set_model_params(qmcb_handle *h, const qmcb_model_params *params)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (!params) FAIL(h, QMCB_ERR_INVALID, "null params");
+    DevModel M{};
+    std::string err;
+    if (!build_model(*params, M, err)) FAIL(h, QMCB_ERR_INVALID, err);
+    if (M.nop != h->M.nop)
+        FAIL(h, QMCB_ERR_INVALID,
+             "boson_number cannot change on a live handle (the launch "
+             "geometry is fixed at qmcb_create)");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    // kernels in flight hold their own copy of the constants (passed by
+    // value), so no synchronisation is needed
+    h->params = *params;
+    h->M = M;
+    return QMCB_OK;
+}
+
+int qmcb_cs_load(qmcb_handle *h, const double *confs, int64_t nconf,
+                 const double *ini_lnpsi)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (nconf < 1 || !confs)
+        FAIL(h, QMCB_ERR_INVALID, "bad confs / nconf");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int N = h->M.nop;
+    cudaFree(h->cs_confs); cudaFree(h->cs_ln0); cudaFree(h->cs_work);
+    h->cs_confs = h->cs_ln0 = h->cs_work = nullptr;
+    h->cs_n = 0;
+    size_t nc = (size_t) nconf * 2 * N * sizeof(double);
+    CUDA_TRY(h, cudaMalloc(&h->cs_confs, nc));
+    CUDA_TRY(h, cudaMalloc(&h->cs_ln0, nconf * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&h->cs_work, (2 * nconf + 4) * sizeof(double)));
+    CUDA_TRY(h, cudaMemcpyAsync(h->cs_confs, confs, nc,
+                                cudaMemcpyHostToDevice, h->stream));
+    if (ini_lnpsi) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->cs_ln0, ini_lnpsi,
+                                    nconf * sizeof(double),
+                                    cudaMemcpyHostToDevice, h->stream));
+    } else {
+        // the set was drawn from the handle's current wave function
+        EvalArgs a{};
+        a.confs = h->cs_confs; a.nconf = nconf; a.lnpsi = h->cs_ln0;
+        int rc = launch_model_eval(h, a, true, false);
+        if (rc) return rc;
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->cs_n = nconf;
+    return QMCB_OK;
+}
+
+int qmcb_cs_variance(qmcb_handle *h, const qmcb_model_params *trial,
+                     double *variance, double *ref_energy, double *lnpsi,
+                     double *energy)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (h->cs_n < 1) FAIL(h, QMCB_ERR_STATE, "qmcb_cs_load not called");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    DevModel M = h->M;
+    if (trial) {
+        std::string err;
+        if (!build_model(*trial, M, err)) FAIL(h, QMCB_ERR_INVALID, err);
+        if (M.nop != h->M.nop)
+            FAIL(h, QMCB_ERR_INVALID, "trial boson_number differs");
+    }
+    const long long n = h->cs_n;
+    double *d_ln = h->cs_work, *d_e = d_ln + n, *d_res = d_e + n;
+    {
+        EvalArgs a{};
+        a.confs = h->cs_confs; a.nconf = n; a.lnpsi = d_ln; a.energy = d_e;
+        long long ctas = (n + h->geom.G - 1) / h->geom.G;
+        int grid = (int) std::min(ctas, (long long) h->sm_count * 32);
+        model_eval_kernel<true, true>
+            <<<grid, h->geom.nthreads, h->geom.smem_bytes, h->stream>>>(
+                M, h->geom, a);
+    }
+    cs_variance_kernel<<<1, CS_THREADS, 0, h->stream>>>(d_ln, h->cs_ln0, d_e,
+                                                        n, d_res);
+    CUDA_TRY(h, cudaGetLastError());
+    double res[4];
+    CUDA_TRY(h, cudaMemcpyAsync(res, d_res, sizeof res,
+                                cudaMemcpyDeviceToHost, h->stream));
+    if (lnpsi)
+        CUDA_TRY(h, cudaMemcpyAsync(lnpsi, d_ln, n * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (energy)
+        CUDA_TRY(h, cudaMemcpyAsync(energy, d_e, n * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (variance) *variance = res[0];
+    if (ref_energy) *ref_energy = res[1];
     return QMCB_OK;
 }
 

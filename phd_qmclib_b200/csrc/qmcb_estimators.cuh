@@ -214,4 +214,261 @@ density_hist_kernel(const double *confs, const int *ref, const int *W_dev,
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// One-body density matrix  g1(sz) = (1/N) sum_i Psi(.., z_i + sz, ..) / Psi
+// of fixed configurations (qmc_base/jastrow/model.py:859-965; the gufunc of
+// PhysicalFuncs :1069-1091 broadcasts it over offsets and configurations).
+//
+// One thread owns one (configuration, offset) item and walks the shifted
+// particle i and its partners j itself, so no cross-thread reduction is
+// needed; the items of a CTA span a few configurations whose column tables
+// (the same far table / four pre-rotated near variants as the step kernel)
+// sit in shared memory, read as warp-wide broadcasts.  ln f2 is never taken
+// per pair: |sin| (far) and |cos| (near) factors are multiplied up with
+// exponent renormalisation and one log per row closes the product.  The
+// unshifted row products are formed once per particle and shared by every
+// offset of the configuration.
+// ---------------------------------------------------------------------------
+constexpr int OBD_ROW_DOUBLES = 15;  // per particle: A 2, V 8, z, ln f1, lf, ln, nnear
+
+// doubles per configuration slot, even so that the double2 tables stay
+// 16-byte aligned
+__host__ __device__ inline size_t obd_slot_doubles(int N)
+{
+    return ((size_t) OBD_ROW_DOUBLES * N + 1) & ~(size_t) 1;
+}
+
+struct ObdArgs {
+    const double *confs;    // [nconf][2][N]
+    long long nconf;
+    const double *offsets;  // [S]
+    int S;
+    double *out;            // [nconf][S]
+};
+
+// Products over the partners j != iskip of a particle with tables
+// (sa, ca, su, cu): lf = ln prod |sin(a - a_j)| / gamma_f over far pairs,
+// ln = ln prod |cos(u - u_j')| over near pairs, nnear = number of near pairs.
+__device__ __forceinline__ void obd_row(const DevModel &M, const double2 *A,
+                                        const double2 *V, int iskip,
+                                        double sa, double ca, double su,
+                                        double cu, double &lf, double &ln,
+                                        int &nnear)
+{
+    const int N = M.nop;
+    const double s_m = M.s_m_scaled;
+    double pf = 1.0, pn = 1.0;
+    int ef = 0, en = 0, nn = 0;
+    for (int j0 = 0; j0 < N; j0 += 4) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = j0 + q;
+            const bool ok = (j < N) && (j != iskip);
+            const int jj = j < N ? j : N - 1;
+            const double2 a = A[jj];
+            const double den_f = fma(sa, a.y, -(ca * a.x));
+            const double cosd = fma(ca, a.y, sa * a.x);
+            // bit 1 = unwrapped (cos >= 0), bit 0 = sigma > 0
+            const unsigned hc = ~(unsigned) __double2hiint(cosd);
+            const unsigned hd = (unsigned) __double2hiint(den_f);
+            const unsigned v = ((hc >> 31) << 1) + ((hc ^ hd) >> 31);
+            const double2 vv = V[jj * 4 + v];
+            const double den_n = fma(cu, vv.y, su * vv.x);
+            const bool near = fabs(den_f) < s_m;
+            pf *= (ok && !near) ? fabs(den_f) : 1.0;
+            pn *= (ok && near) ? fabs(den_n) : 1.0;
+            nn += (ok && near) ? 1 : 0;
+        }
+        renorm(pf, ef);
+        renorm(pn, en);
+    }
+    lf = log(pf) + ef * LN2;
+    ln = log(pn) + en * LN2;
+    nnear = nn;
+}
+
+__global__ void obd_kernel(DevModel M, ObdArgs a)
+{
+    extern __shared__ __align__(16) double obd_smem[];
+    const int N = M.nop, S = a.S;
+    const long long wtot = a.nconf * S;
+    const long long w0 = (long long) blockIdx.x * blockDim.x;
+    if (w0 >= wtot) return;
+    const long long wl = (w0 + blockDim.x < wtot ? w0 + blockDim.x : wtot) - 1;
+    const long long c0 = w0 / S;
+    const int nc = (int) (wl / S - c0) + 1;
+    const size_t slot = obd_slot_doubles(N);
+    // tables of the configurations this CTA touches
+    for (int e = threadIdx.x; e < nc * N; e += blockDim.x) {
+        const int g = e / N, i = e - g * N;
+        double *base = obd_smem + g * slot;
+        double2 *A = reinterpret_cast<double2 *>(base);
+        double2 *V = A + N;
+        double *zs = base + 10 * (size_t) N;
+        const double z = a.confs[(c0 + g) * 2 * N + i];
+        zs[i] = z;
+        if (!M.is_ideal) {
+            double sa, ca, su, cu;
+            particle_tables(M, recast(z, 0.0, M.L), sa, ca, su, cu);
+            A[i] = make_double2(sa * M.inv_gam, ca * M.inv_gam);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const int w = (v & 2) ? 0 : 1;
+                const double cp = M.cpsi[w];
+                const double sp = (v & 1) ? M.spsi[w] : -M.spsi[w];
+                V[i * 4 + v] = make_double2(fma(su, cp, cu * sp),
+                                            fma(cu, cp, -(su * sp)));
+            }
+        }
+    }
+    __syncthreads();
+    // unshifted row products and ln f1, once per particle
+    for (int e = threadIdx.x; e < nc * N; e += blockDim.x) {
+        const int g = e / N, i = e - g * N;
+        double *base = obd_smem + g * slot;
+        const double2 *A = reinterpret_cast<const double2 *>(base);
+        const double2 *V = A + N;
+        double *zs = base + 10 * (size_t) N;
+        const double z = zs[i];
+        double ln1 = 0.0, lf = 0.0, ln = 0.0;
+        int nnear = 0;
+        if (!M.is_free) ln1 = one_body<true>(M, z).lnf;
+        if (!M.is_ideal) {
+            double sa, ca, su, cu;
+            particle_tables(M, recast(z, 0.0, M.L), sa, ca, su, cu);
+            obd_row(M, A, V, i, sa, ca, su, cu, lf, ln, nnear);
+        }
+        zs[N + i] = ln1;
+        zs[2 * N + i] = lf;
+        zs[3 * N + i] = ln;
+        reinterpret_cast<int *>(zs + 4 * N)[i] = nnear;
+    }
+    __syncthreads();
+    const long long w = w0 + threadIdx.x;
+    if (w >= wtot) return;
+    const long long c = w / S;
+    const int s = (int) (w - c * S);
+    const double *base = obd_smem + (size_t) (c - c0) * slot;
+    const double2 *A = reinterpret_cast<const double2 *>(base);
+    const double2 *V = A + N;
+    const double *zs = base + 10 * (size_t) N;
+    const int *cnt = reinterpret_cast<const int *>(zs + 4 * N);
+    const double sz = a.offsets[s];
+    double acc = 0.0;
+    // the reference returns 0 (not exp(0)) per particle for the free ideal
+    // gas (qmc_base/jastrow/model.py:891-892)
+    if (!(M.is_free && M.is_ideal)) {
+        for (int i = 0; i < N; ++i) {
+            const double zsft = zs[i] + sz;
+            double lnr = 0.0;
+            if (!M.is_free)
+                lnr = one_body<true>(M, zsft).lnf - zs[N + i];
+            if (!M.is_ideal) {
+                double sa, ca, su, cu, lf, ln;
+                int nnear;
+                particle_tables(M, recast(zsft, 0.0, M.L), sa, ca, su, cu);
+                obd_row(M, A, V, i, sa, ca, su, cu, lf, ln, nnear);
+                const int dn = nnear - cnt[i];
+                lnr += M.beta * ((lf - zs[2 * N + i]) - dn * M.ln_gam)
+                       + (ln - zs[3 * N + i]) + dn * M.ln_am;
+            }
+            acc += exp(lnr);
+        }
+    }
+    a.out[w] = acc / N;
+}
+
+
+// ---------------------------------------------------------------------------
+// rho_k of fixed configurations at ARBITRARY momenta (the gufunc
+// PhysicalFuncs.fourier_density, qmc_base/jastrow/model.py:1093-1122, takes
+// any kz_set; the samplers only use k_m = 2 pi m / L, which ssf_eval_kernel
+// covers).  One thread per (configuration, momentum); out [nconf][nk][2] =
+// (Re, Im) = (sum cos kz z_i, sum sin kz z_i) summed in particle order.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+fdk_general_kernel(const double *confs, long long nconf, int N,
+                   const double *kz, int nk, double *out)
+{
+    const long long total = nconf * nk;
+    for (long long e = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+         e < total; e += (long long) gridDim.x * blockDim.x) {
+        const long long b = e / nk;
+        const double k = kz[e - b * nk];
+        const double *z = confs + b * 2 * N;
+        double sc = 0.0, ss = 0.0;
+        for (int i = 0; i < N; ++i) {
+            double s, c;
+            sincos(k * z[i], &s, &c);
+            sc += c;
+            ss += s;
+        }
+        out[2 * e] = sc;
+        out[2 * e + 1] = ss;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Correlated-sampling objective of the wave-function optimiser
+// (CSWFOptimizer.weighed_variance, qmc_base/jastrow/model.py:1147-1165):
+//   w_c = exp(2 (ln|Psi_trial| - ln|Psi_0|)_c - max),  E_ref = <E>_w,
+//   variance = <(E - E_ref)^2>_w.
+// One CTA, fixed-order tree reductions: the result does not depend on
+// scheduling.  out = {variance, E_ref, sum w, sum w^2}.
+// ---------------------------------------------------------------------------
+constexpr int CS_THREADS = 1024;
+
+template <typename Op>
+__device__ __forceinline__ double cs_block_reduce(double v, double *red, Op op)
+{
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = CS_THREADS / 2; s > 0; s >>= 1) {
+        if ((int) threadIdx.x < s)
+            red[threadIdx.x] = op(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    double r = red[0];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(CS_THREADS)
+cs_variance_kernel(const double *lnpsi, const double *lnpsi0,
+                   const double *energy, long long n, double *out)
+{
+    __shared__ double red[CS_THREADS];
+    auto fmaxop = [](double a, double b) { return a > b ? a : b; };
+    auto addop = [](double a, double b) { return a + b; };
+    double m = -INFINITY;
+    for (long long c = threadIdx.x; c < n; c += CS_THREADS)
+        m = fmaxop(m, 2.0 * (lnpsi[c] - lnpsi0[c]));
+    m = cs_block_reduce(m, red, fmaxop);
+    double sw = 0.0, swe = 0.0, sw2 = 0.0;
+    for (long long c = threadIdx.x; c < n; c += CS_THREADS) {
+        double w = exp(2.0 * (lnpsi[c] - lnpsi0[c]) - m);
+        sw += w;
+        swe = fma(w, energy[c], swe);
+        sw2 = fma(w, w, sw2);
+    }
+    sw = cs_block_reduce(sw, red, addop);
+    swe = cs_block_reduce(swe, red, addop);
+    sw2 = cs_block_reduce(sw2, red, addop);
+    const double eref = swe / sw;
+    double sv = 0.0;
+    for (long long c = threadIdx.x; c < n; c += CS_THREADS) {
+        double w = exp(2.0 * (lnpsi[c] - lnpsi0[c]) - m);
+        double d = energy[c] - eref;
+        sv = fma(w, d * d, sv);
+    }
+    sv = cs_block_reduce(sv, red, addop);
+    if (threadIdx.x == 0) {
+        out[0] = sv / sw;
+        out[1] = eref;
+        out[2] = sw;
+        out[3] = sw2;
+    }
+}
+
 }  // namespace qmcb

@@ -158,6 +158,96 @@ class Engine:
         self._check(rc, 'qmcb_fourier_density')
         return out
 
+    def one_body_density(self, confs, offsets):
+        """``confs`` (B, 2, N) or (2, N), ``offsets`` (S,) -> (B, S): the
+        one-body density matrix estimator of each configuration at each
+        displacement.  Reference: ``core_funcs.one_body_density``
+        (``qmc_base/jastrow/model.py:934-965``).
+        """
+        confs = _f64(confs)
+        if confs.ndim == 2:
+            confs = confs[None]
+        if confs.ndim != 3 or confs.shape[1:] != (2, self.nop):
+            raise ValueError(f'confs must have shape (B, 2, {self.nop})')
+        offsets = _f64(np.atleast_1d(offsets))
+        if offsets.ndim != 1:
+            raise ValueError('offsets must be one-dimensional')
+        out = np.empty((confs.shape[0], offsets.shape[0]))
+        rc = self._L.qmcb_one_body_density(
+            self._h, ptr(confs), confs.shape[0], ptr(offsets),
+            offsets.shape[0], ptr(out))
+        self._check(rc, 'qmcb_one_body_density')
+        return out
+
+    def one_body_density_device(self, d_confs, nconf, d_offsets, num_offsets,
+                                d_out):
+        """Device-pointer variant, asynchronous on the engine's stream."""
+        rc = self._L.qmcb_one_body_density_device(
+            self._h, C.c_void_p(d_confs), nconf, C.c_void_p(d_offsets),
+            num_offsets, C.c_void_p(d_out))
+        self._check(rc, 'qmcb_one_body_density_device')
+
+    def fourier_density_k(self, confs, kz_set):
+        """``confs`` (B, 2, N), ``kz_set`` (K,) -> complex (B, K): rho_k at
+        arbitrary momenta.  Reference: ``PhysicalFuncs.fourier_density``
+        (``qmc_base/jastrow/model.py:1093-1122``)."""
+        confs = _f64(confs)
+        if confs.ndim == 2:
+            confs = confs[None]
+        if confs.ndim != 3 or confs.shape[1:] != (2, self.nop):
+            raise ValueError(f'confs must have shape (B, 2, {self.nop})')
+        kz = _f64(np.atleast_1d(kz_set))
+        out = np.empty((confs.shape[0], kz.shape[0], 2))
+        rc = self._L.qmcb_fourier_density_k(self._h, ptr(confs),
+                                            confs.shape[0], ptr(kz),
+                                            kz.shape[0], ptr(out))
+        self._check(rc, 'qmcb_fourier_density_k')
+        return out[..., 0] + 1j * out[..., 1]
+
+    # -- trial-wave-function optimisation -----------------------------------
+    def set_model_params(self, spec):
+        """Swap the model scalars of the live handle (same boson number)."""
+        block = param_block(spec)
+        mp = _lib.model_params_struct(block)
+        rc = self._L.qmcb_set_model_params(self._h, C.byref(mp))
+        self._check(rc, 'qmcb_set_model_params')
+        self.block = block
+        self.supercell_size = float(block[4])
+
+    def cs_load(self, sys_conf_set, ini_wf_abs_log_set=None):
+        """Keep the optimiser's configuration set on the device."""
+        confs = _f64(sys_conf_set)
+        if confs.ndim != 3 or confs.shape[1:] != (2, self.nop):
+            raise ValueError(f'confs must have shape (B, 2, {self.nop})')
+        ln0 = None
+        if ini_wf_abs_log_set is not None:
+            ln0 = _f64(ini_wf_abs_log_set)
+            if ln0.shape != (confs.shape[0],):
+                raise ValueError('ini_wf_abs_log_set must have one entry per '
+                                 'configuration')
+        rc = self._L.qmcb_cs_load(self._h, ptr(confs), confs.shape[0],
+                                  ptr(ln0))
+        self._check(rc, 'qmcb_cs_load')
+        self._cs_n = confs.shape[0]
+
+    def cs_variance(self, trial_spec=None, want_sets=False):
+        """Weighted variance of E_L over the loaded set under the trial
+        parameters -> dict(variance, ref_energy[, wf_abs_log, energy])."""
+        mp = None
+        if trial_spec is not None:
+            mp = C.byref(_lib.model_params_struct(param_block(trial_spec)))
+        var, eref = C.c_double(), C.c_double()
+        n = getattr(self, '_cs_n', 0)
+        ln = np.empty(n) if want_sets else None
+        en = np.empty(n) if want_sets else None
+        rc = self._L.qmcb_cs_variance(self._h, mp, C.byref(var),
+                                      C.byref(eref), ptr(ln), ptr(en))
+        self._check(rc, 'qmcb_cs_variance')
+        out = dict(variance=var.value, ref_energy=eref.value)
+        if want_sets:
+            out.update(wf_abs_log=ln, energy=en)
+        return out
+
     # -- DMC ----------------------------------------------------------------
     @staticmethod
     def dmc_params(time_step, max_num_walkers, target_num_walkers,

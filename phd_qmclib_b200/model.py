@@ -316,3 +316,169 @@ def param_block(spec) -> np.ndarray:
     if len(flat) != NUM_PARAMS:
         raise ValueError(f'expected {NUM_PARAMS} parameters, got {len(flat)}')
     return np.array(flat, dtype=np.float64)
+
+
+def _evolve(spec, **changes):
+    """``attr.evolve`` for a reference (attrs) Spec, ``dataclasses.replace``
+    for this module's."""
+    if hasattr(type(spec), '__attrs_attrs__'):
+        import attr
+        return attr.evolve(spec, **changes)
+    from dataclasses import replace
+    return replace(spec, **changes)
+
+
+class PhysicalFuncs:
+    """Batched physical properties of a model spec on the GPU: the
+    reference's ``PhysicalFuncs`` (``mrbp_qmc/model.py:801-814``,
+    gufuncs in ``qmc_base/jastrow/model.py:1007-1122``) with the same
+    call signatures and NumPy broadcasting over leading dimensions.
+
+    ``spec`` may be this module's :class:`Spec`, a reference ``Spec``, or a
+    ``(params, obf_params, tbf_params)`` triple (the reference's
+    ``cfc_spec_nt``).
+    """
+
+    def __init__(self, cfc_spec_nt, device: int = 0):
+        self.cfc_spec_nt = cfc_spec_nt
+        self._device = device
+        self._engine = None
+
+    @classmethod
+    def from_model_spec(cls, model_spec, device: int = 0):
+        """Reference: ``PhysicalFuncs.from_model_spec``
+        (``mrbp_qmc/model.py:806-809``)."""
+        return cls(model_spec.cfc_spec, device)
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            from .engine import Engine
+            self._engine = Engine(self.cfc_spec_nt, self._device)
+        return self._engine
+
+    def _batch(self, sys_conf):
+        confs = np.asarray(sys_conf, dtype=np.float64)
+        nop = self.engine.nop
+        if confs.ndim < 2 or confs.shape[-2:] != (len(SysConfSlot), nop):
+            raise ValueError(
+                f'sys_conf must have shape (..., {len(SysConfSlot)}, {nop})')
+        lead = confs.shape[:-2]
+        return np.ascontiguousarray(confs.reshape((-1,) + confs.shape[-2:])), lead
+
+    def wf_abs_log(self, sys_conf):
+        """``(ns,nop)->()``: ln|Psi| (``jastrow/model.py:1019-1043``)."""
+        confs, lead = self._batch(sys_conf)
+        out = self.engine.model_eval(confs, want=('lnpsi',))['lnpsi']
+        return out.reshape(lead)[()]
+
+    def energy(self, sys_conf):
+        """``(ns,nop)->()``: local energy (``jastrow/model.py:1045-1067``)."""
+        confs, lead = self._batch(sys_conf)
+        out = self.engine.model_eval(confs, want=('energy',))['energy']
+        return out.reshape(lead)[()]
+
+    def one_body_density(self, sz, sys_conf):
+        """``(),(ns,nop)->()``: one-body density matrix estimator
+        (``jastrow/model.py:1069-1091``); ``sz`` broadcasts against the
+        leading dimensions of ``sys_conf``."""
+        confs, lead = self._batch(sys_conf)
+        sz = np.asarray(sz, dtype=np.float64)
+        offsets, inv = np.unique(sz.ravel(), return_inverse=True)
+        table = self.engine.one_body_density(confs, offsets)    # (B, S)
+        b_idx = np.arange(confs.shape[0]).reshape(lead)
+        s_idx = inv.reshape(sz.shape)
+        b_idx, s_idx = np.broadcast_arrays(b_idx, s_idx)
+        return table[b_idx, s_idx][()]
+
+    def fourier_density(self, kz_set, sys_conf):
+        """``(nkz),(ns,nop)->(nkz)``: complex rho_k
+        (``jastrow/model.py:1093-1122``)."""
+        confs, lead = self._batch(sys_conf)
+        kz_set = np.asarray(kz_set, dtype=np.float64)
+        if kz_set.ndim != 1:
+            raise ValueError('kz_set must be one-dimensional')
+        out = self.engine.fourier_density_k(confs, kz_set)
+        return out.reshape(lead + (kz_set.shape[0],))
+
+
+class CSWFOptimizer:
+    """Correlated-sampling optimiser of the trial wave function: minimises
+    the weighted variance of the local energy over a fixed configuration set
+    as a function of ``tbf_contact_cutoff``.  Interface of the reference's
+    ``CSWFOptimizer`` (``mrbp_qmc/model.py:817-942``,
+    ``qmc_base/jastrow/model.py:1125-1211``); the configuration set stays on
+    the GPU and each trial value costs one model-evaluation launch plus one
+    reduction launch instead of a dask bag over the configurations.
+    ``use_threads`` / ``num_workers`` are accepted for compatibility and
+    ignored.
+    """
+
+    def __init__(self, spec, sys_conf_set, ini_wf_abs_log_set,
+                 ref_energy=None, use_threads=True, num_workers=None,
+                 verbose=False, device: int = 0):
+        self.spec = spec
+        self.sys_conf_set = np.asarray(sys_conf_set, dtype=np.float64)
+        self.ini_wf_abs_log_set = np.asarray(ini_wf_abs_log_set,
+                                             dtype=np.float64)
+        self.ref_energy = ref_energy
+        self.use_threads = use_threads
+        self.num_workers = num_workers
+        self.verbose = verbose
+        self._device = device
+        self._engine = None
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            from .engine import Engine
+            self._engine = Engine(self.spec, self._device)
+            self._engine.cs_load(self.sys_conf_set, self.ini_wf_abs_log_set)
+        return self._engine
+
+    def update_spec(self, tbf_contact_cutoff: float):
+        """Reference: ``mrbp_qmc/model.py:852-862``."""
+        return _evolve(self.spec,
+                       tbf_contact_cutoff=float(tbf_contact_cutoff))
+
+    @staticmethod
+    def weighed_variance(weights_log_set, energy_set, ref_energy=None):
+        """Host restatement kept for API compatibility
+        (``jastrow/model.py:1147-1165``); the optimiser itself reduces on
+        the device."""
+        weights_log_set = np.asarray(weights_log_set)
+        energy_set = np.asarray(energy_set)
+        rel_weights = np.exp(weights_log_set - weights_log_set.max())
+        weight_sum = rel_weights.sum()
+        ref_energy = (rel_weights * energy_set).sum() / weight_sum
+        e_diff = rel_weights * (energy_set - ref_energy) ** 2
+        return e_diff.sum() / weight_sum
+
+    def wf_abs_log_and_energy_set(self, cfc_spec):
+        """ln|Psi| and E_L of every configuration under ``cfc_spec``
+        (``mrbp_qmc/model.py:889-903``)."""
+        res = self.engine.cs_variance(cfc_spec, want_sets=True)
+        return res['wf_abs_log'], res['energy']
+
+    def principal_function(self, tbf_contact_cutoff):
+        """The weighted variance at a trial cutoff
+        (``jastrow/model.py:1186-1206``)."""
+        tbf_contact_cutoff = float(np.ravel(tbf_contact_cutoff)[0])
+        trial = self.update_spec(tbf_contact_cutoff)
+        return self.engine.cs_variance(trial)['variance']
+
+    @property
+    def principal_function_bounds(self):
+        """Reference: ``mrbp_qmc/model.py:905-914``."""
+        sc_size = self.spec.supercell_size
+        return [(5e-2, (0.5 - 5e-3) * sc_size)]
+
+    def exec(self, **de_kwargs):
+        """Differential evolution over the cutoff on the host
+        (``mrbp_qmc/model.py:929-942``); returns the updated spec."""
+        from scipy.optimize import differential_evolution
+        opt = differential_evolution(self.principal_function,
+                                     bounds=self.principal_function_bounds,
+                                     disp=self.verbose, **de_kwargs)
+        opt_cutoff, = opt.x
+        return self.update_spec(opt_cutoff)

@@ -47,6 +47,120 @@ def test_model_eval_vs_oracle_bulk(eng_mod, oracle, name, nconf):
     assert maxnorm_err(o['drift'], ref['drift']) < TOL
 
 
+@pytest.mark.parametrize('name', golden_names('model_'))
+def test_one_body_density_vs_reference(eng_mod, name):
+    """g1(sz) of the live reference (qmc_base/jastrow/model.py:934-965) at
+    offsets inside, at and far beyond the box."""
+    g = golden(name)
+    nobd = g['obd'].shape[0]
+    with eng_mod.Engine((g['params'][:12], g['params'][12:19],
+                         g['params'][19:])) as eng:
+        o = eng.one_body_density(g['confs'][:nobd], g['obd_offsets'])
+    assert o.shape == g['obd'].shape
+    assert rel_err(o, g['obd']) < TOL
+
+
+@pytest.mark.parametrize('name,nconf,noff', [
+    ('lat_n100', 37, 50), ('lat_n50', 300, 7), ('odd_n7', 1000, 1),
+    ('frac_n21', 11, 301), ('deep_n200', 9, 33), ('ideal_n8', 50, 16),
+    ('strong_n10', 129, 128)])
+def test_one_body_density_vs_oracle_bulk(eng_mod, oracle, name, nconf, noff):
+    """Item counts that do not divide the CTA size: a CTA's items straddle
+    several configurations, and the last CTA is ragged."""
+    g = golden('model_' + name + '.npz')
+    p = g['params']
+    nop, size = int(p[3]), float(p[4])
+    rng = np.random.default_rng(11)
+    confs = np.zeros((nconf, 2, nop))
+    confs[:, 0] = rng.random((nconf, nop)) * size
+    offsets = (rng.random(noff) - 0.5) * 3 * size
+    offsets[0] = 0.0
+    ref = oracle.one_body_density(p, confs, offsets)
+    with eng_mod.Engine((p[:12], p[12:19], p[19:])) as eng:
+        o = eng.one_body_density(confs, offsets)
+        assert eng.one_body_density(confs[:0], offsets).shape == (0, noff)
+        assert eng.one_body_density(confs, offsets[:0]).shape == (nconf, 0)
+    assert rel_err(o, ref) < TOL
+    if not (p[10] != 0 and p[11] != 0):
+        assert np.all(o[:, 0] == 1.0)       # zero displacement: exactly 1
+
+
+@pytest.mark.parametrize('name', golden_names('model_'))
+def test_physical_funcs_vs_reference(name):
+    """The PhysicalFuncs mirror (gufunc signatures and broadcasting of
+    qmc_base/jastrow/model.py:1007-1122) against the live reference."""
+    from phd_qmclib_b200 import model
+    g = golden(name)
+    p = g['params']
+    pf = model.PhysicalFuncs((p[:12], p[12:19], p[19:]))
+    confs = g['confs']
+    assert scaled_err(pf.wf_abs_log(confs), g['lnpsi']) < TOL
+    assert scaled_err(pf.energy(confs), g['energy']) < TOL
+    assert np.ndim(pf.energy(confs[0])) == 0
+    nobd = g['obd'].shape[0]
+    # (S,1) against (B,2,N) broadcasts to (S,B)
+    obd = pf.one_body_density(g['obd_offsets'][:, None], confs[:nobd])
+    assert obd.shape == (len(g['obd_offsets']), nobd)
+    assert rel_err(obd.T, g['obd']) < TOL
+    assert rel_err(pf.one_body_density(g['obd_offsets'][2], confs[1]),
+                   g['obd'][1, 2]) < TOL
+    fk = pf.fourier_density(g['kz_set'], confs.reshape((2, -1) + confs.shape[1:]))
+    assert fk.shape == (2, confs.shape[0] // 2, len(g['kz_set']))
+    assert np.max(np.abs(fk.reshape(g['fdk_k'].shape) - g['fdk_k'])) \
+        < TOL * confs.shape[2]
+    pf.engine.close()
+
+
+@pytest.mark.parametrize('name', golden_names('cswf_'))
+def test_cs_optimizer_vs_reference(name):
+    """principal_function of the GPU optimiser against the reference's
+    correlated-sampling variance at each frozen trial cutoff."""
+    from phd_qmclib_b200 import model
+    g = golden(name)
+    kw = dict(zip([str(k) for k in g['spec_keys']], g['spec_vals']))
+    spec = model.Spec(**kw)
+    opt = model.CSWFOptimizer(spec, g['confs'], g['ini_lnpsi'])
+    for k, rm in enumerate(g['cutoffs']):
+        var = opt.principal_function(rm)
+        scale = max(g['variance'][k], TOL * np.mean(g['energy'][k] ** 2))
+        assert abs(var - g['variance'][k]) < 1e-9 * scale, (rm, var)
+        ln, en = opt.wf_abs_log_and_energy_set(opt.update_spec(rm).cfc_spec)
+        assert scaled_err(ln, g['lnpsi'][k]) < TOL
+        assert scaled_err(en, g['energy'][k]) < TOL
+    # the handle's own parameters are untouched by trial evaluations
+    res = opt.engine.cs_variance(None, want_sets=True)
+    assert scaled_err(res['wf_abs_log'], g['ini_lnpsi']) < TOL
+    # ini_lnpsi = NULL: evaluated on the device with the current parameters
+    opt.engine.cs_load(g['confs'], None)
+    v2 = opt.engine.cs_variance(opt.update_spec(g['cutoffs'][1]))['variance']
+    scale = max(g['variance'][1], TOL * np.mean(g['energy'][1] ** 2))
+    assert abs(v2 - g['variance'][1]) < 1e-9 * scale
+    # swapping the parameters of the live handle
+    opt.engine.set_model_params(opt.update_spec(g['cutoffs'][-1]))
+    o = opt.engine.model_eval(g['confs'], want=('lnpsi', 'energy'))
+    assert scaled_err(o['lnpsi'], g['lnpsi'][-1]) < TOL
+    assert scaled_err(o['energy'], g['energy'][-1]) < TOL
+    opt.engine.close()
+
+
+def test_cs_optimizer_exec_finds_minimum():
+    """exec(): differential evolution on the host over the device objective
+    (mrbp_qmc/model.py:929-942) lands on the minimum of a scan."""
+    from phd_qmclib_b200 import model
+    g = golden('cswf_odd_n7.npz')
+    kw = dict(zip([str(k) for k in g['spec_keys']], g['spec_vals']))
+    spec = model.Spec(**kw)
+    opt = model.CSWFOptimizer(spec, g['confs'], g['ini_lnpsi'])
+    lo, hi = opt.principal_function_bounds[0]
+    scan = np.linspace(lo, hi, 60)
+    vals = np.array([opt.principal_function(r) for r in scan])
+    best = opt.exec(seed=1, maxiter=30, popsize=12, tol=1e-8)
+    assert isinstance(best, model.Spec)
+    assert lo <= best.tbf_contact_cutoff <= hi
+    assert opt.principal_function(best.tbf_contact_cutoff) <= vals.min() + 1e-9
+    opt.engine.close()
+
+
 def _run_both(eng_mod, oracle, p, ini, wmax, target, dt, nwc, seed, nts,
               nblocks, energy_mode=0):
     size = float(p[4])

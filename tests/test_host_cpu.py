@@ -93,3 +93,26 @@ def test_vmc_sampling_surface():
     assert vmc.SamplingBlock._fields == ('iter_props', 'iter_ssf',
                                          'accept_rate', 'last_state')
     assert smp.core_funcs.init_props_data_block((2,)).move_stat.dtype == bool
+
+
+def test_cswf_optimizer_host_surface():
+    """Spec derivation for the trial cutoffs of the optimiser matches the
+    reference's attr.evolve + Spec.tbf_params (the 25 scalars frozen in the
+    cswf fixtures); no device needed."""
+    from conftest import golden, golden_names
+    from phd_qmclib_b200 import model
+    for name in golden_names('cswf_'):
+        g = golden(name)
+        kw = dict(zip([str(k) for k in g['spec_keys']], g['spec_vals']))
+        spec = model.Spec(**kw)
+        opt = model.CSWFOptimizer(spec, g['confs'], g['ini_lnpsi'])
+        lo, hi = opt.principal_function_bounds[0]
+        assert lo == 5e-2 and hi == (0.5 - 5e-3) * spec.supercell_size
+        for rm, block in zip(g['cutoffs'], g['trial_params']):
+            trial = opt.update_spec(rm)
+            assert trial.tbf_contact_cutoff == rm
+            got = model.param_block(trial)
+            assert np.max(np.abs(got - block) / np.maximum(np.abs(block), 1e-300)) < 1e-10
+        v = model.CSWFOptimizer.weighed_variance(
+            2 * (g['lnpsi'][0] - g['ini_lnpsi']), g['energy'][0])
+        assert abs(v - g['variance'][0]) <= 1e-12 * abs(g['variance'][0])

@@ -21,6 +21,23 @@ def test_model_eval(oracle, name):
     obd = oracle.one_body_density(g['params'], g['confs'][:nobd],
                                   g['obd_offsets'])
     assert rel_err(obd, g['obd']) < 1e-12
+    fk = oracle.fourier_density_k(g['params'], g['confs'], g['kz_set'])
+    assert np.max(np.abs(fk - g['fdk_k'])) < 1e-12 * g['confs'].shape[2]
+
+
+@pytest.mark.parametrize('name', golden_names('cswf_'))
+def test_cs_variance(oracle, name):
+    """Correlated-sampling objective: ln|Psi|, E_L of the fixed set under
+    each trial cutoff and the reference's weighed_variance."""
+    g = golden(name)
+    for k, block in enumerate(g['trial_params']):
+        o = oracle.model_eval(block, g['confs'])
+        assert rel_err(o['lnpsi'], g['lnpsi'][k]) < TOL
+        assert rel_err(o['energy'], g['energy'][k]) < TOL
+        var, _ = oracle.weighed_variance(o['lnpsi'], g['ini_lnpsi'],
+                                         o['energy'])
+        scale = max(g['variance'][k], 1e-12 * np.mean(g['energy'][k] ** 2))
+        assert abs(var - g['variance'][k]) < 1e-9 * scale
 
 
 @pytest.mark.parametrize('name', golden_names('dmc_step_'))
