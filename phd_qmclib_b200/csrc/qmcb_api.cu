@@ -465,6 +465,48 @@ int ensure_est_log(qmcb_handle *h, long long nts)
     return QMCB_OK;
 }
 
+// rho_k of `rows` configurations: staged-seed kernel when a walker's chunks
+// fit one CTA, the exact-seed kernel otherwise (M > 2048).
+int launch_ssf_eval(qmcb_handle *h, const SsfArgs &a, long long rows)
+{
+    const int N = a.N, M = a.M;
+    const int nchunk = (M + SSF_CHUNK - 1) / SSF_CHUNK;
+    static const bool force_exact = getenv("QMCB_SSF_EXACT_SEEDS") != nullptr;
+    if (nchunk <= SSF_THREADS && !force_exact) {
+        SsfStage st{};
+        st.nchunk = nchunk;
+        st.G = std::max(1, SSF_THREADS / nchunk);
+        // ~40 KB of seeds per CTA (5 CTAs per SM next to 96 registers)
+        const size_t budget = 40 * 1024;
+        st.P = (int) (budget / ((size_t) st.G * (nchunk + 1) * 16));
+        st.P = std::max(1, std::min(st.P, std::min(N, 32)));
+        if (const char *ep = getenv("QMCB_SSF_P"))
+            st.P = std::max(1, std::min(atoi(ep), N));
+        while (st.G > 1 && ssf_stage_smem(st.G, nchunk, st.P) > 96 * 1024)
+            --st.G;
+        size_t smem = ssf_stage_smem(st.G, nchunk, st.P);
+        if (smem > 48 * 1024)
+            CUDA_TRY(h, cudaFuncSetAttribute(
+                            ssf_eval_staged_kernel,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int) smem));
+        int grid = (int) std::min<long long>((rows + st.G - 1) / st.G,
+                                             (long long) h->sm_count * 16);
+        ssf_eval_staged_kernel<<<std::max(grid, 1), SSF_THREADS, smem,
+                                 h->stream>>>(a, st);
+    } else {
+        int G = std::max(1, SSF_THREADS / nchunk);
+        G = std::min(G, std::max(1, (40 * 1024) / (24 * N)));
+        size_t smem = (size_t) 3 * G * N * sizeof(double);
+        int grid = (int) std::min<long long>((rows + G - 1) / G,
+                                             (long long) h->sm_count * 16);
+        ssf_eval_kernel<<<std::max(grid, 1), SSF_THREADS, smem, h->stream>>>(
+            a, G, nchunk);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return QMCB_OK;
+}
+
 // One step of the S(k) estimator on the "actual" population
 // (qmc_base/jastrow/dmc.py:363-573): step_idx counts from the block start.
 int launch_ssf_step(qmcb_handle *h, long long step_idx)
@@ -488,12 +530,8 @@ int launch_ssf_step(qmcb_handle *h, long long step_idx)
         a.ref = B.ref; a.W_dev = W_dev; a.N = N; a.M = M;
         a.two_over_L = 2.0 / h->M.L;
         a.out = out; a.prev = prev; a.accumulate = pure ? 1 : 0;
-        int nchunk = (M + SSF_CHUNK - 1) / SSF_CHUNK;
-        int G = std::max(1, SSF_THREADS / nchunk);
-        G = std::min(G, std::max(1, (40 * 1024) / (24 * N)));
-        size_t smem = (size_t) 3 * G * N * sizeof(double);
-        int grid = std::min((B.cap + G - 1) / G, h->sm_count * 16);
-        ssf_eval_kernel<<<grid, SSF_THREADS, smem, h->stream>>>(a, G, nchunk);
+        int rc = launch_ssf_eval(h, a, B.cap);
+        if (rc) return rc;
     }
     RowRange rr{};
     rr.hi_dev = W_dev; rr.lo_host = 0;
@@ -748,14 +786,8 @@ int qmcb_fourier_density(qmcb_handle *h, const double *confs, int64_t nconf,
     a.confs = d_confs; a.W_host = nconf; a.N = N; a.M = M;
     a.two_over_L = 2.0 / h->M.L;
     a.out = d_out;
-    int nchunk = (M + SSF_CHUNK - 1) / SSF_CHUNK;
-    int G = std::max(1, SSF_THREADS / nchunk);
-    G = std::min(G, std::max(1, (40 * 1024) / (24 * N)));
-    size_t smem = (size_t) 3 * G * N * sizeof(double);
-    int grid = (int) std::min<long long>((nconf + G - 1) / G,
-                                         h->sm_count * 16);
-    ssf_eval_kernel<<<grid, SSF_THREADS, smem, h->stream>>>(a, G, nchunk);
-    CUDA_TRY(h, cudaGetLastError());
+    rc = launch_ssf_eval(h, a, nconf);
+    if (rc) return rc;
     CUDA_TRY(h, cudaMemcpyAsync(out, d_out, no * sizeof(double),
                                 cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));

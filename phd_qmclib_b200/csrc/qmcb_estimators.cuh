@@ -107,6 +107,108 @@ ssf_eval_kernel(SsfArgs a, int G, int nchunk)
     }
 }
 
+// Same result, cheaper seeds (the exact sincospi seed above is ~80
+// instructions per particle and chunk, more than the 64 of the recurrence it
+// starts).  Particles are taken in batches of P; for each one a stager thread
+// evaluates e^{i theta} and e^{i 16 theta} exactly and walks the geometric
+// sequence e^{i 16 j theta}, j = 0..nchunk-1, by complex multiplication (one
+// rounding per step: <= nchunk ulp) into shared memory, from where the chunk
+// threads pick their seed with one LDS.128.  Requires G * nchunk <= blockDim.
+struct SsfStage {
+    int G, nchunk, P;
+};
+
+__host__ __device__ inline size_t ssf_stage_smem(int G, int nchunk, int P)
+{
+    return (size_t) G * P * (nchunk + 1) * sizeof(double2);
+}
+
+__global__ void __launch_bounds__(SSF_THREADS)
+ssf_eval_staged_kernel(SsfArgs a, SsfStage st)
+{
+    extern __shared__ __align__(16) double ssf_smem[];
+    const long long W = a.W_dev ? (long long) *a.W_dev : a.W_host;
+    const int N = a.N, G = st.G, nchunk = st.nchunk, P = st.P;
+    double2 *seeds = reinterpret_cast<double2 *>(ssf_smem);  // [G][P][nchunk]
+    double2 *cs = seeds + (size_t) G * P * nchunk;           // [G][P] (c1, s1)
+    const int t = threadIdx.x;
+    const bool worker = t < G * nchunk;
+    const int g = worker ? t / nchunk : 0, j = worker ? t - g * nchunk : 0;
+    const int m0 = j * SSF_CHUNK;
+    for (long long s0 = (long long) blockIdx.x * G; s0 < W;
+         s0 += (long long) gridDim.x * G) {
+        const long long s = s0 + g;
+        const bool live = worker && s < W;
+        double re[SSF_CHUNK], im[SSF_CHUNK];
+#pragma unroll
+        for (int q = 0; q < SSF_CHUNK; ++q) { re[q] = 0.0; im[q] = 0.0; }
+        for (int b0 = 0; b0 < N; b0 += P) {
+            const int np = min(P, N - b0);
+            __syncthreads();        // the previous batch has been consumed
+            for (int e = t; e < G * np; e += blockDim.x) {
+                const int gg = e / np, ii = e - gg * np;
+                const long long ss = s0 + gg;
+                if (ss >= W) continue;
+                const long long r = a.ref ? (long long) a.ref[ss] : ss;
+                const double x = a.confs[r * 2 * N + b0 + ii] * a.two_over_L;
+                double s1, c1, sb, cb;
+                sincospi(x, &s1, &c1);
+                sincospi((double) SSF_CHUNK * x, &sb, &cb);
+                cs[gg * P + ii] = make_double2(c1, s1);
+                double2 *row = seeds + ((size_t) gg * P + ii) * nchunk;
+                double cr = 1.0, ci = 0.0;
+                for (int jj = 0; jj < nchunk; ++jj) {
+                    row[jj] = make_double2(cr, ci);
+                    const double nr = fma(cr, cb, -(ci * sb));
+                    const double ni = fma(cr, sb, ci * cb);
+                    cr = nr; ci = ni;
+                }
+            }
+            __syncthreads();
+            if (live) {
+                const double2 *sd = seeds + (size_t) g * P * nchunk + j;
+                const double2 *pc = cs + g * P;
+                for (int ii = 0; ii < np; ++ii) {
+                    const double2 e0 = sd[(size_t) ii * nchunk];
+                    const double2 c = pc[ii];
+                    double cm = e0.x, sm = e0.y;
+                    const double twoc = 2.0 * c.x;
+                    double cp = fma(cm, c.x, sm * c.y);      // mode m0 - 1
+                    double sp = fma(sm, c.x, -(cm * c.y));
+#pragma unroll
+                    for (int q = 0; q < SSF_CHUNK; ++q) {
+                        re[q] += cm;
+                        im[q] += sm;
+                        double cn = fma(twoc, cm, -cp);
+                        double sn = fma(twoc, sm, -sp);
+                        cp = cm; sp = sm; cm = cn; sm = sn;
+                    }
+                }
+            }
+        }
+        if (live) {
+            double *o = a.out + (s * a.M + m0) * 3;
+            const double *pv = nullptr;
+            if (a.accumulate) {
+                long long r = a.ref ? (long long) a.ref[s] : s;
+                pv = a.prev + (r * a.M + m0) * 3;
+            }
+#pragma unroll
+            for (int q = 0; q < SSF_CHUNK; ++q) {
+                if (m0 + q < a.M) {
+                    double v0 = fma(re[q], re[q], im[q] * im[q]);
+                    double v1 = re[q], v2 = im[q];
+                    if (pv) {
+                        v0 += pv[3 * q]; v1 += pv[3 * q + 1];
+                        v2 += pv[3 * q + 2];
+                    }
+                    o[3 * q] = v0; o[3 * q + 1] = v1; o[3 * q + 2] = v2;
+                }
+            }
+        }
+    }
+}
+
 // Pure-estimator transport after the forward-walking window:
 // out[s] = prev[ref[s]] (qmc_base/jastrow/dmc.py:441-447).
 __global__ void rows_gather_kernel(const double *prev, const int *ref,
@@ -141,7 +243,16 @@ colsum_partial_kernel(const double *a, RowRange rr, int ncol, double *partial)
     const long long r1 = (r0 + per < hi) ? r0 + per : hi;
     for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
         double acc = 0.0;
-        for (long long r = r0; r < r1; ++r) acc += a[r * ncol + c];
+        long long r = r0;
+        // eight loads in flight, added in row order (same sum as a plain loop)
+        for (; r + 8 <= r1; r += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = a[(r + u) * ncol + c];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += v[u];
+        }
+        for (; r < r1; ++r) acc += a[r * ncol + c];
         partial[(long long) blockIdx.x * ncol + c] = acc;
     }
 }
@@ -154,7 +265,16 @@ __global__ void colsum_final_kernel(const double *partial, int nblk, int ncol,
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncol) return;
     double acc = 0.0;
-    for (int b = 0; b < nblk; ++b) acc += partial[(long long) b * ncol + c];
+    int b = 0;
+    for (; b + 8 <= nblk; b += 8) {     // eight loads in flight, same order
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            v[u] = partial[(long long) (b + u) * ncol + c];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; b < nblk; ++b) acc += partial[(long long) b * ncol + c];
     double v = partial_sign * acc;
     if (base) v += base[c];
     out[c] = v * scale;
