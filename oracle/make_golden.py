@@ -337,36 +337,97 @@ def gen_vmc_blocks(mrbp, name, kwargs, rng, draw_uniform, *, move_spread,
     print(f'vmc_blocks_{name}: accept={rec["accept_rate"]}')
 
 
+def _ref_reblock(series):
+    """mean and mean_eff_error of a series from the reference's OWN blocking
+    analysis (stats/reblock.py:113-217, 327-420)."""
+    import warnings
+    from phd_qmclib.stats import reblock
+    obj = reblock.Object(np.ascontiguousarray(series, dtype=np.float64))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        return float(obj.mean), float(obj.mean_eff_error)
+
+
 def gen_dmc_stat(mrbp, name, kwargs, *, n_target, wmax, dt, nts, nblocks,
-                 burn, seed, nwc=0.125):
-    """A longer serial reference DMC run: per-block sums for the
-    statistical parity test (reblocked error bars)."""
+                 burn, seed, nwc=0.125, num_modes=8):
+    """A longer serial reference DMC run: per-block sums of the energy and of
+    the mixed S(k) estimator for the statistical parity tests, with the
+    error bars of the reference's own reblocking."""
     model, dmc = mrbp.model, mrbp.dmc
     spec = model.Spec(**kwargs)
     nop = spec.boson_number
+    ssf_spec = dmc.SSFEstSpec(num_modes, as_pure_est=False,
+                              pfw_num_time_steps=nts)
     sampling = dmc.Sampling(spec, dt, wmax, n_target,
                             num_walkers_control_factor=nwc, rng_seed=seed,
-                            jit_parallel=False)
+                            ssf_est_spec=ssf_spec, jit_parallel=False)
     rng = np.random.default_rng(seed)
     confs = np.zeros((n_target, 2, nop))
     confs[:, 0, :] = rng.random((n_target, nop)) * spec.supercell_size
     ini_state = sampling.build_state(confs)
-    e_sum, w_sum = [], []
+    e_sum, w_sum, s_sum = [], [], []
     for b, block in zip(range(burn + nblocks),
                         sampling.blocks(ini_state, nts, burn)):
         if b < burn:
             continue
         e_sum.append(block.iter_props.energy.sum())
         w_sum.append(block.iter_props.weight.sum())
-    e_sum, w_sum = np.array(e_sum), np.array(w_sum)
+        s_sum.append(np.asarray(block.iter_ssf).sum(axis=0))
+    e_sum, w_sum, s_sum = np.array(e_sum), np.array(w_sum), np.array(s_sum)
+    # ratio estimators, linearised per block, through the reference reblock
+    e_mean = e_sum.sum() / w_sum.sum()
+    _, e_err = _ref_reblock((e_sum - e_mean * w_sum) / w_sum.mean())
+    sk_mean = s_sum[:, :, 0].sum(axis=0) / w_sum.sum()
+    sk_err = np.array([
+        _ref_reblock((s_sum[:, m, 0] - sk_mean[m] * w_sum) / w_sum.mean())[1]
+        for m in range(num_modes)])
     out = dict(params=param_block(spec), ini_confs=confs, n_target=n_target,
                max_num_walkers=wmax, time_step=dt, nts=nts, nblocks=nblocks,
                burn=burn, nwc_factor=nwc, block_energy=e_sum,
-               block_weight=w_sum)
+               block_weight=w_sum, block_ssf=s_sum, num_modes=num_modes,
+               ref_energy_mean=e_mean, ref_energy_err=e_err,
+               ref_sk_mean=sk_mean, ref_sk_err=sk_err)
     np.savez_compressed(os.path.join(GOLDEN, f'dmc_stat_{name}.npz'), **out)
     epn = e_sum / w_sum / nop
-    print(f'dmc_stat_{name}: E/N = {epn.mean():.6f} +- '
-          f'{epn.std(ddof=1) / math.sqrt(len(epn)):.6f} (naive)')
+    print(f'dmc_stat_{name}: E/N = {e_mean / nop:.6f} +- {e_err / nop:.6f} '
+          f'(reference reblock; naive {epn.std(ddof=1) / math.sqrt(len(epn)):.6f})'
+          f' <|rho_k|^2>/N = {sk_mean / nop}')
+
+
+def gen_vmc_stat(mrbp, name, kwargs, *, move_spread, ns, nblocks, burn, seed,
+                 num_modes=8):
+    """A long single-chain reference VMC run (qmc_base/vmc.py:557-770):
+    per-block means of E_L and of |rho_k|^2 with the error bars of the
+    reference's own reblocking."""
+    model, vmc = mrbp.model, mrbp.vmc
+    spec = model.Spec(**kwargs)
+    nop = spec.boson_number
+    sampling = vmc.Sampling(spec, move_spread, rng_seed=seed,
+                            ssf_est_spec=vmc.SSFEstSpec(num_modes))
+    rng = np.random.default_rng(seed)
+    conf = spec.get_sys_conf_buffer()
+    conf[0, :] = rng.random(nop) * spec.supercell_size
+    ini_state = sampling.build_state(conf)
+    e_blk, s_blk, acc = [], [], []
+    for b, block in zip(range(burn + nblocks),
+                        sampling.blocks(ns, ini_state)):
+        if b < burn:
+            continue
+        e_blk.append(block.iter_props.energy.mean())
+        s_blk.append(np.asarray(block.iter_ssf)[:, :, 0].mean(axis=0))
+        acc.append(block.accept_rate)
+    e_blk, s_blk = np.array(e_blk), np.array(s_blk)
+    e_mean, e_err = _ref_reblock(e_blk)
+    sk = [_ref_reblock(s_blk[:, m]) for m in range(num_modes)]
+    out = dict(params=param_block(spec), ini_conf=conf,
+               move_spread=move_spread, ns=ns, nblocks=nblocks, burn=burn,
+               num_modes=num_modes, block_energy=e_blk, block_ssf=s_blk,
+               accept_rate=np.array(acc), ref_energy_mean=e_mean,
+               ref_energy_err=e_err, ref_sk_mean=np.array([m for m, _ in sk]),
+               ref_sk_err=np.array([e for _, e in sk]))
+    np.savez_compressed(os.path.join(GOLDEN, f'vmc_stat_{name}.npz'), **out)
+    print(f'vmc_stat_{name}: E/N = {e_mean / nop:.6f} +- {e_err / nop:.6f} '
+          f'acc = {np.mean(acc):.4f}')
 
 
 def gen_cswf(mrbp, name, kwargs, rng, *, nconf, cutoffs):
@@ -463,6 +524,11 @@ def main():
             interaction_strength=2, boson_number=16, supercell_size=16,
             tbf_contact_cutoff=4), n_target=512, wmax=640, dt=2e-3, nts=256,
             nblocks=48, burn=12, seed=11)
+        gen_vmc_stat(mrbp, 'll_n16', SPECS['ll_n16'], move_spread=0.25,
+                     ns=4096, nblocks=64, burn=4, seed=1)
+        gen_vmc_stat(mrbp, 'defects_n20', SPECS['defects_n20'],
+                     move_spread=0.25 * (1 / 1.5), ns=4096, nblocks=64,
+                     burn=4, seed=2)
 
 
 if __name__ == '__main__':

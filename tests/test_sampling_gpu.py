@@ -172,25 +172,99 @@ def test_dmc_energy_vs_reference_run(name):
         boundaries = (0.0, float(p[4]))
         sys_conf_shape = (2, nop)
 
+    num_modes = int(g['num_modes'])
     smp = dmc.Sampling(_Spec, float(g['time_step']),
                        int(g['max_num_walkers']), int(g['n_target']),
                        num_walkers_control_factor=float(g['nwc_factor']),
-                       rng_seed=2024)
+                       rng_seed=2024,
+                       ssf_est_spec=dmc.SSFEstSpec(num_modes, False, nts))
     it = smp.blocks(smp.build_state(g['ini_confs']), nts, burn)
     for _ in islice(it, burn):
         pass
     # four times the reference's length: the engine's error bar is the
     # smaller of the two
-    e_sum, w_sum = [], []
+    e_sum, w_sum, s_sum = [], [], []
     for _, blk in zip(range(4 * nblocks), it):
         e_sum.append(blk.iter_props.energy.sum())
         w_sum.append(blk.iter_props.weight.sum())
+        s_sum.append(np.asarray(blk.iter_ssf)[:, :, 0].sum(axis=0))
     e_eng, err_eng = ratio_mean_error(e_sum, w_sum)
+    # the reference side: the larger of its own reblocking error
+    # (stats/reblock.py, frozen in the fixture) and our blocking of its series
+    err_ref = max(err_ref, float(g['ref_energy_err']))
+    assert e_ref == pytest.approx(float(g['ref_energy_mean']), rel=1e-12)
     sigma = np.hypot(err_ref, err_eng)
+    print(f'dmc {name} E/N: {e_eng / nop:.5f} vs {e_ref / nop:.5f}, '
+          f'z = {(e_eng - e_ref) / sigma:+.2f}')
     assert abs(e_eng - e_ref) < 4 * sigma, (e_eng / nop, e_ref / nop,
                                             sigma / nop)
+    # mixed S(k) estimator: <|rho_k|^2> per mode (north star: S(k) within
+    # combined error bars); k = 0 is N^2 identically
+    s_sum = np.array(s_sum)
+    for m in range(num_modes):
+        sk_ref, sk_err_ref = ratio_mean_error(g['block_ssf'][:, m, 0],
+                                              g['block_weight'])
+        sk_err_ref = max(sk_err_ref, float(g['ref_sk_err'][m]))
+        sk_eng, sk_err_eng = ratio_mean_error(s_sum[:, m], w_sum)
+        if m == 0:
+            assert sk_eng == pytest.approx(nop ** 2, rel=1e-12)
+            assert sk_ref == pytest.approx(nop ** 2, rel=1e-12)
+            continue
+        sig = np.hypot(sk_err_ref, sk_err_eng)
+        print(f'dmc {name} S(k) mode {m}: z = {(sk_eng - sk_ref) / sig:+.2f}')
+        assert abs(sk_eng - sk_ref) < 4.5 * sig, (m, sk_eng, sk_ref, sig)
     # and the quirk-free textbook weight (energy_mode=1) is measurably lower
     # (SURVEY.md H1): the reference's semantics are what we match
+
+
+@pytest.mark.parametrize('name', ['ll_n16', 'defects_n20'])
+def test_vmc_energy_and_ssf_vs_reference_run(name):
+    """Statistical parity of VMC (north star): energy and <|rho_k|^2> of a
+    batch of independent engine chains against one long chain of the LIVE
+    reference (oracle/make_golden.py: gen_vmc_stat; error bars of the
+    reference from its own stats/reblock.py)."""
+    from phd_qmclib_b200 import model, vmc
+    g = golden(f'vmc_stat_{name}.npz')
+    spec = model.Spec(**SPECS[name])
+    nop, num_modes = spec.boson_number, int(g['num_modes'])
+    nch, ns = 96, 512
+    smp = vmc.Sampling(spec, float(g['move_spread']), rng_seed=77,
+                       ssf_est_spec=vmc.SSFEstSpec(num_modes))
+    ini = smp.build_state(_ini(spec, nch, 21))
+    sums = smp.block_sums(ns, ini)
+    for _ in range(32):                     # equilibration: 16384 steps
+        next(sums)
+    nblk = 24
+    e = np.zeros(nch)
+    sk = np.zeros((nch, num_modes))
+    acc = 0.0
+    for _ in range(nblk):
+        o = next(sums)
+        e += o['sum_energy'][:, 0] / ns
+        sk += o['sum_ssf'][:, :, 0] / ns
+        acc += o['accept_rate'].mean()
+    e /= nblk
+    sk /= nblk
+    # chains are independent: the error of the mean is the spread over chains
+    e_eng, e_err = e.mean(), e.std(ddof=1) / np.sqrt(nch)
+    sig = np.hypot(e_err, float(g['ref_energy_err']))
+    print(f'vmc {name} E/N: {e_eng / nop:.5f} vs '
+          f'{float(g["ref_energy_mean"]) / nop:.5f}, '
+          f'z = {(e_eng - float(g["ref_energy_mean"])) / sig:+.2f}')
+    assert abs(e_eng - float(g['ref_energy_mean'])) < 4 * sig, (
+        e_eng / nop, float(g['ref_energy_mean']) / nop, sig / nop)
+    assert acc / nblk == pytest.approx(float(np.mean(g['accept_rate'])),
+                                       abs=0.02)
+    for m in range(num_modes):
+        m_eng, m_err = sk[:, m].mean(), sk[:, m].std(ddof=1) / np.sqrt(nch)
+        if m == 0:
+            assert m_eng == pytest.approx(nop ** 2, rel=1e-12)
+            continue
+        sig = np.hypot(m_err, float(g['ref_sk_err'][m]))
+        print(f'vmc {name} S(k) mode {m}: '
+              f'z = {(m_eng - float(g["ref_sk_mean"][m])) / sig:+.2f}')
+        assert abs(m_eng - float(g['ref_sk_mean'][m])) < 4.5 * sig, (
+            m, m_eng, float(g['ref_sk_mean'][m]), sig)
 
 
 def test_vmc_single_chain_like_reference(oracle):
