@@ -186,6 +186,41 @@ class CoreFuncs:
 core_funcs = CoreFuncs()
 
 
+def local_capacity(max_num_walkers: int, world_size: int) -> int:
+    """Slots per rank when ``max_num_walkers`` global slots are sharded."""
+    return -(-int(max_num_walkers) // int(world_size))
+
+
+def slab_bounds(n: int, world_size: int, rank: int) -> t.Tuple[int, int]:
+    """[lo, hi) of rank's contiguous slab of ``n`` ordered walkers; sizes
+    differ by at most one, the larger slabs first (the layout
+    ``qmcb_rebalance_plan`` restores)."""
+    base, extra = divmod(int(n), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def allreduce_sum(dist, arrays) -> None:
+    """In-place sum over the ranks of a list of float64 numpy arrays through
+    an initialised ``torch.distributed`` process group (plumbing: NCCL
+    reduces device tensors, gloo host tensors)."""
+    import torch
+    if not arrays:
+        return
+    flat = np.concatenate([np.asarray(a, dtype=np.float64).ravel()
+                           for a in arrays])
+    t_ = torch.from_numpy(flat)
+    on_gpu = str(dist.get_backend()) == 'nccl'
+    if on_gpu:
+        t_ = t_.cuda()
+    dist.all_reduce(t_)
+    flat = t_.cpu().numpy()
+    off = 0
+    for a in arrays:
+        a[...] = flat[off:off + a.size].reshape(a.shape)
+        off += a.size
+
+
 @dataclass(frozen=True)
 class Sampling:
     """A DMC sampling (reference mrbp_qmc/dmc.py:143-334).
@@ -195,7 +230,19 @@ class Sampling:
     accepted for signature compatibility and ignored.  Engine-only options:
     ``device`` (CUDA ordinal), ``energy_mode`` (0 = the reference's
     stale-slot energy in the branching weight; 1 = the parent's
-    energy), ``eager_last_state`` (copy the State back after every block).
+    energy), ``eager_last_state`` (copy the State back after every block),
+    ``dist`` (an initialised ``torch.distributed``-like module: one process
+    per GPU, the walkers sharded over the ranks).
+
+    With ``dist``: ``max_num_walkers`` / ``target_num_walkers`` stay GLOBAL;
+    rank r owns the r-th contiguous slab of the ensemble in
+    ``local_capacity`` slots, so the global ensemble is the ordered
+    concatenation of the slabs.  A State then holds the local
+    slab (confs, props, num_walkers) next to the GLOBAL scalars (energy,
+    weight, ref_energy, accum_energy); the per-step series of a block are
+    global, the estimator tables are all-reduced once per block, and the
+    populations are evened out by order-preserving neighbour shifts before
+    each block.
     """
     model_spec: t.Any
     time_step: float
@@ -210,11 +257,15 @@ class Sampling:
     device: int = 0
     energy_mode: int = 0
     eager_last_state: bool = False
+    dist: t.Any = None
     _cache: dict = field(default_factory=dict, init=False, repr=False,
                          compare=False)
 
     def __post_init__(self):
         if self.rng_seed is None:
+            if self.world_size > 1:
+                raise ValueError('rng_seed must be given (and equal on every '
+                                 'rank) when the walkers are sharded')
             seed = int(np.random.SeedSequence().generate_state(1)[0])
             object.__setattr__(self, 'rng_seed', seed)
         if self.num_walkers_control_factor is None:
@@ -264,13 +315,27 @@ class Sampling:
         return (np.arange(self.ssf_est_spec.num_modes) * 2 * math.pi
                 / self.model_spec.supercell_size)
 
+    # -- sharding ---------------------------------------------------------------
+    @property
+    def world_size(self) -> int:
+        return int(self.dist.get_world_size()) if self.dist is not None else 1
+
+    @property
+    def rank(self) -> int:
+        return int(self.dist.get_rank()) if self.dist is not None else 0
+
+    @property
+    def local_capacity(self) -> int:
+        """Slots on this rank."""
+        return local_capacity(self.max_num_walkers, self.world_size)
+
     @property
     def state_confs_shape(self):
-        return (self.max_num_walkers,) + tuple(self.model_spec.sys_conf_shape)
+        return (self.local_capacity,) + tuple(self.model_spec.sys_conf_shape)
 
     @property
     def state_props_shape(self):
-        return self.max_num_walkers,
+        return self.local_capacity,
 
     @property
     def core_funcs(self) -> CoreFuncs:
@@ -280,7 +345,10 @@ class Sampling:
     @property
     def engine(self) -> Engine:
         if 'engine' not in self._cache:
-            self._cache['engine'] = Engine(self.model_spec, self.device)
+            eng = Engine(self.model_spec, self.device)
+            if self.world_size > 1:
+                eng.comm_init_torch(self.dist, self.rank, self.world_size)
+            self._cache['engine'] = eng
         return self._cache['engine']
 
     def _engine_params(self, target_num_walkers=None):
@@ -291,6 +359,8 @@ class Sampling:
             target_num_walkers or self.target_num_walkers,
             self.num_walkers_control_factor, self.rng_seed, z_min, z_max,
             energy_mode=self.energy_mode,
+            local_capacity=(self.local_capacity if self.world_size > 1
+                            else 0),
             ssf=None if sp.assume_none else (
                 sp.num_modes, sp.as_pure_est,
                 min(int(sp.pfw_num_time_steps), _BIG_NTS)),
@@ -310,7 +380,12 @@ class Sampling:
             raise StateError("sys_conf_set is not a valid set of "
                              "configurations of the model spec")
         sys_conf_set = sys_conf_set[-self.target_num_walkers:]
-        n, wmax = len(sys_conf_set), self.max_num_walkers
+        world, rank = self.world_size, self.rank
+        if world > 1:
+            # every rank is handed the same global set and keeps its slab
+            lo, hi = slab_bounds(len(sys_conf_set), world, rank)
+            sys_conf_set = sys_conf_set[lo:hi]
+        n, wmax = len(sys_conf_set), self.local_capacity
         if n > wmax:
             raise StateError('more configurations than max_num_walkers')
         ev = self.engine.model_eval(sys_conf_set, want=('energy', 'drift'))
@@ -323,8 +398,10 @@ class Sampling:
         energy[:n] = ev['energy']
         weight[:n] = 1.0
         mask[:n] = False
-        state_energy = float((energy[:n] * weight[:n]).sum())
-        state_weight = float(weight[:n].sum())
+        sums = np.array([(energy[:n] * weight[:n]).sum(), weight[:n].sum()])
+        if world > 1:
+            allreduce_sum(self.dist, [sums])
+        state_energy, state_weight = float(sums[0]), float(sums[1])
         mean_energy = state_energy / state_weight
         if ref_energy is None:
             ref_energy = mean_energy
@@ -342,7 +419,7 @@ class Sampling:
         if int(live.sum()) != n or not live[:n].all():
             raise StateError('the live walkers of a state must occupy its '
                              'first num_walkers slots')
-        if len(props.energy) != self.max_num_walkers:
+        if len(props.energy) != self.local_capacity:
             raise StateError('state was built for another max_num_walkers')
         sc = _lib.StateScalars()
         sc.energy = float(ini_state.energy)
@@ -352,14 +429,15 @@ class Sampling:
         sc.total_energy = 0.0
         sc.total_weight = 0.0
         sc.num_walkers = n
-        sc.max_num_walkers = self.max_num_walkers
+        sc.max_num_walkers = self.local_capacity
         sc.step = 0
         sc.capacity_hits = 0
         self.engine.dmc_set_state(
             self._engine_params(target_num_walkers),
             np.asarray(ini_state.confs)[:n],
             np.asarray(props.energy)[:n], np.asarray(props.weight)[:n], sc,
-            slot_energy=np.asarray(props.energy, dtype=np.float64))
+            slot_energy=np.asarray(props.energy, dtype=np.float64),
+            global_slot_offset=self.rank * self.local_capacity)
 
     def _fetch_state(self, stamp=None) -> State:
         eng = self.engine
@@ -369,7 +447,7 @@ class Sampling:
                              'use eager_last_state=True')
         s = eng.dmc_get_state()
         sc = s['scalars']
-        bs = BranchingSpec(np.zeros(self.max_num_walkers, dtype=np.int64),
+        bs = BranchingSpec(np.zeros(self.local_capacity, dtype=np.int64),
                            s['cloning_ref'])
         return State(s['confs'],
                      StateProps(s['energy'], s['weight'],
@@ -394,7 +472,7 @@ class Sampling:
         walker count (qmc_base/dmc.py:1009), not ``target_num_walkers``."""
         nts = int(num_time_steps_block)
         self._load_state(ini_state, int(ini_state.num_walkers))
-        wmax = self.max_num_walkers
+        wmax = self.local_capacity
         while True:
             confs = np.zeros((nts,) + self.state_confs_shape)
             energy = np.zeros((nts, wmax))
@@ -433,10 +511,20 @@ class Sampling:
                              else (nts, dp.num_bins, 1))
             i_ssf = np.zeros((1, 1, 3) if sp.assume_none
                              else (nts, sp.num_modes, 3))
+            if self.world_size > 1 and block_idx > 0:
+                # even out the slabs; done here, not after the block, so
+                # that last_state of the previous block stays readable
+                eng.dmc_rebalance()
             eng.dmc_run_block(
                 nts, eval_estimators=est, out=out,
                 density=None if dp.assume_none else i_den,
                 ssf=None if sp.assume_none else i_ssf)
+            if self.world_size > 1 and est:
+                # the engine returns this rank's partial sums
+                allreduce_sum(self.dist,
+                              [a for a, none in ((i_den, dp.assume_none),
+                                                 (i_ssf, sp.assume_none))
+                               if not none])
             stamp = self._cache['stamp'] = object()
             blk = SamplingBlock(props, i_den, i_ssf,
                                 lambda s=stamp: self._fetch_state(s))

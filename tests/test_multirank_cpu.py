@@ -126,3 +126,79 @@ def test_rebalance_over_gloo(counts):
     sizes = [len(r[1]) for r in res]
     assert max(sizes) - min(sizes) <= 1                        # balanced
     assert len({round(r[3], 9) for r in res}) == 1             # same E_ref
+
+
+def _sampling_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from phd_qmclib_b200 import dmc, model
+        spec = model.Spec(0, 1, 4, 16, 16, 4)
+        smp = dmc.Sampling(spec, 1e-3, 101, 64, rng_seed=5, dist=dist,
+                           ssf_est_spec=dmc.SSFEstSpec(4))
+        assert (smp.world_size, smp.rank) == (world, rank)
+        cap = smp.local_capacity
+        assert cap == -(-101 // world)
+        assert smp.state_confs_shape == (cap, 2, 16)
+        assert smp._engine_params().local_capacity == cap
+        lo, hi = dmc.slab_bounds(64, world, rank)
+        # estimator tables: every rank contributes its partial sums
+        den = np.full((3, 5, 1), float(rank + 1))
+        ssf = np.arange(3 * 4 * 3, dtype=np.float64).reshape(3, 4, 3) * (rank + 1)
+        sums = np.array([10.0 * (rank + 1), float(hi - lo)])
+        dmc.allreduce_sum(dist, [den, ssf])
+        dmc.allreduce_sum(dist, [sums])
+        q.put((rank, lo, hi, den.copy(), ssf.copy(), sums.copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_sampling_shards_and_reduces(world):
+    """Host logic of the sharded dmc.Sampling: contiguous slabs that tile the
+    ensemble in order, local capacity, and the per-block all-reduce of the
+    estimator tables (gloo stands in for NCCL)."""
+    port = _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sampling_worker, args=(r, world, port, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)],
+                 key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    tri = world * (world + 1) / 2
+    edges = [0]
+    for rank, lo, hi, den, ssf, sums in res:
+        assert lo == edges[-1] and hi - lo in (64 // world, 64 // world + 1)
+        edges.append(hi)
+        assert np.all(den == tri)
+        assert np.array_equal(
+            ssf, np.arange(36, dtype=np.float64).reshape(3, 4, 3) * tri)
+        assert sums[0] == 10.0 * tri and sums[1] == 64
+    assert edges[-1] == 64
+
+
+def test_sampling_sharded_needs_a_seed():
+    from phd_qmclib_b200 import dmc, model
+
+    class _Dist:
+        @staticmethod
+        def get_world_size():
+            return 4
+
+        @staticmethod
+        def get_rank():
+            return 1
+
+    spec = model.Spec(0, 1, 4, 16, 16, 4)
+    with pytest.raises(ValueError):
+        dmc.Sampling(spec, 1e-3, 100, 64, dist=_Dist)
+    smp = dmc.Sampling(spec, 1e-3, 100, 64, rng_seed=1, dist=_Dist)
+    assert smp.local_capacity == 25 and smp.state_props_shape == (25,)
+    assert [dmc.slab_bounds(10, 4, r) for r in range(4)] == [
+        (0, 3), (3, 6), (6, 8), (8, 10)]
