@@ -70,6 +70,8 @@ if __name__ == '__main__':
         print(json.dumps(vmc_c2()), flush=True)
     if 'c3' in which:
         print(json.dumps(dmc(50, 10000, 512, 5 * PI ** 2, label='C3 DMC N=50 1e4 walkers')), flush=True)
+    if 'c3big' in which:
+        print(json.dumps(dmc(50, 250000, 128, 5 * PI ** 2, label='DMC N=50 2.5e5 walkers (population scaling of C3)')), flush=True)
     if 'c5' in which:
         print(json.dumps(dmc(200, 31250, 64, 20 * PI ** 2, label='C5 DMC N=200 3.1e4 walkers/GPU, no estimators', dt=5e-4)), flush=True)
     if 'c5e' in which:
