@@ -808,7 +808,7 @@ int qmcb_one_body_density_device(qmcb_handle *h, const double *d_confs,
     const int N = h->M.nop, S = num_offsets;
     // items (configuration, offset) are dealt to CTAs in order; a CTA needs
     // the tables of every configuration its items touch
-    int nt = 128;
+    int nt = 128, per_conf = 0;
     size_t smem = 0;
     for (; nt >= 32; nt /= 2) {
         int gmax = (nt - 1) / S + 2;
@@ -816,9 +816,15 @@ int qmcb_one_body_density_device(qmcb_handle *h, const double *d_confs,
         smem = (size_t) gmax * obd_slot_doubles(N) * sizeof(double);
         if (smem <= (size_t) h->max_smem) break;
     }
-    if (nt < 32)
-        FAIL(h, QMCB_ERR_INVALID,
-             "boson_number too large for the one-body density tables");
+    if (nt < 32) {
+        // large N: the tables of a single configuration per CTA
+        nt = 128;
+        per_conf = 1;
+        smem = obd_slot_doubles(N) * sizeof(double);
+        if (smem > (size_t) h->max_smem)
+            FAIL(h, QMCB_ERR_INVALID,
+                 "boson_number too large for the one-body density tables");
+    }
     if (smem > 48 * 1024)
         CUDA_TRY(h, cudaFuncSetAttribute(
                         obd_kernel,
@@ -827,8 +833,10 @@ int qmcb_one_body_density_device(qmcb_handle *h, const double *d_confs,
     ObdArgs a{};
     a.confs = d_confs; a.nconf = nconf; a.offsets = d_offsets; a.S = S;
     a.out = d_out;
+    a.per_conf = per_conf;
     long long items = (long long) nconf * S;
-    long long grid = (items + nt - 1) / nt;
+    long long grid = per_conf ? (long long) nconf * ((S + nt - 1) / nt)
+                              : (items + nt - 1) / nt;
     if (grid > 0x7fffffffll)
         FAIL(h, QMCB_ERR_INVALID, "too many (configuration, offset) items");
     obd_kernel<<<(unsigned) grid, nt, smem, h->stream>>>(h->M, a);

@@ -365,6 +365,8 @@ struct ObdArgs {
     const double *offsets;  // [S]
     int S;
     double *out;            // [nconf][S]
+    int per_conf;           // 1: a CTA's items belong to ONE configuration
+                            // (large N: tables of one configuration at a time)
 };
 
 // Products over the partners j != iskip of a particle with tables
@@ -413,9 +415,19 @@ __global__ void obd_kernel(DevModel M, ObdArgs a)
     extern __shared__ __align__(16) double obd_smem[];
     const int N = M.nop, S = a.S;
     const long long wtot = a.nconf * S;
-    const long long w0 = (long long) blockIdx.x * blockDim.x;
-    if (w0 >= wtot) return;
-    const long long wl = (w0 + blockDim.x < wtot ? w0 + blockDim.x : wtot) - 1;
+    long long w0, wl;       // first and last item of this CTA
+    if (a.per_conf) {
+        const int nchunk = (S + blockDim.x - 1) / blockDim.x;
+        const long long c = blockIdx.x / nchunk;
+        const int s0 = (int) (blockIdx.x - c * nchunk) * blockDim.x;
+        if (c >= a.nconf) return;
+        w0 = c * S + s0;
+        wl = c * S + (s0 + (int) blockDim.x < S ? s0 + (int) blockDim.x : S) - 1;
+    } else {
+        w0 = (long long) blockIdx.x * blockDim.x;
+        if (w0 >= wtot) return;
+        wl = (w0 + blockDim.x < wtot ? w0 + blockDim.x : wtot) - 1;
+    }
     const long long c0 = w0 / S;
     const int nc = (int) (wl / S - c0) + 1;
     const size_t slot = obd_slot_doubles(N);
@@ -466,7 +478,7 @@ __global__ void obd_kernel(DevModel M, ObdArgs a)
     }
     __syncthreads();
     const long long w = w0 + threadIdx.x;
-    if (w >= wtot) return;
+    if (w > wl) return;
     const long long c = w / S;
     const int s = (int) (w - c * S);
     const double *base = obd_smem + (size_t) (c - c0) * slot;

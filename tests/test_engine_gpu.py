@@ -419,3 +419,59 @@ def test_dmc_restart_is_bit_exact(eng_mod):
         assert np.array_equal(sa[k], sb[k]), k
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize('nop', [1, 2, 5, 33, 257, 400, 1000])
+def test_size_extremes_vs_oracle(eng_mod, oracle, nop):
+    """From a single particle (no pairs at all) to a walker that fills a
+    whole 256-thread CTA (nb = 250 particle blocks): lnPsi, E_L, drift, rho_k,
+    g1 and two DMC steps against the oracle."""
+    from phd_qmclib_b200 import model
+    size = float(max(nop, 2))
+    spec = model.Spec(3 * np.pi ** 2, 1, 2.5, nop, size, 0.25 * size)
+    p = model.param_block(spec)
+    rng = np.random.default_rng(nop)
+    nconf = 6 if nop >= 257 else 40
+    confs = np.zeros((nconf, 2, nop))
+    confs[:, 0] = rng.random((nconf, nop)) * size
+    ref = oracle.model_eval(p, confs)
+    with eng_mod.Engine(spec) as eng:
+        o = eng.model_eval(confs)
+        assert scaled_err(o['lnpsi'], ref['lnpsi']) < TOL
+        assert scaled_err(o['energy'], ref['energy']) < TOL
+        assert maxnorm_err(o['drift'], ref['drift']) < TOL
+        # empty batches are a no-op, not an error
+        e = eng.model_eval(confs[:0])
+        assert e['lnpsi'].shape == (0,) and e['drift'].shape == (0, nop)
+        modes = 5
+        s = eng.fourier_density(confs, modes)
+        assert np.max(np.abs(s - oracle.fourier_density(p, confs, modes))) \
+            < 1e-12 * nop ** 2
+        offs = np.array([0.0, 0.3, -1.2 * size])
+        g1 = eng.one_body_density(confs[:3], offs)
+        assert rel_err(g1, oracle.one_body_density(p, confs[:3], offs)) < 1e-11
+        if nop == 1000:
+            # one configuration per CTA, several CTAs per configuration
+            offs = np.linspace(-0.5 * size, 0.5 * size, 130)
+            g1 = eng.one_body_density(confs[:2], offs)
+            assert rel_err(g1, oracle.one_body_density(p, confs[:2], offs)) \
+                < 1e-11
+        wmax = nconf + 4
+        dp = eng.dmc_params(1e-3, wmax, nconf, 0.125, 5, 0.0, size)
+        eng.dmc_init(dp, confs)
+        b = eng.dmc_run_block(2)
+    st = oracle.DMCState(p, confs, wmax)
+    a = st.run_block(5, 1e-3, nconf, 0.125, 2, 0.0, size)
+    assert np.array_equal(a['num_walkers'], b['num_walkers'])
+    for k in ('energy', 'weight', 'ref_energy', 'accum_energy'):
+        assert rel_err(b[k], a[k]) < 1e-9, k
+
+
+def test_too_many_particles_is_an_error(eng_mod):
+    """Beyond 256 particle blocks a walker no longer fits one CTA: the
+    engine says so at creation instead of computing something else."""
+    from phd_qmclib_b200 import model
+    from phd_qmclib_b200._lib import EngineError
+    spec = model.Spec(10.0, 1, 2, 1028, 1028.0, 257.0)
+    with pytest.raises(EngineError, match='too large'):
+        eng_mod.Engine(spec)
