@@ -68,6 +68,8 @@ if __name__ == '__main__':
     which = sys.argv[1:] or ['c2', 'c3', 'c5', 'c5e']
     if 'c2' in which:
         print(json.dumps(vmc_c2()), flush=True)
+    if 'c2s' in which:      # short blocks: what an ncu replay can afford
+        print(json.dumps(vmc_c2(ns=16, nblocks=3)), flush=True)
     if 'c3' in which:
         print(json.dumps(dmc(50, 10000, 512, 5 * PI ** 2, label='C3 DMC N=50 1e4 walkers')), flush=True)
     if 'c3big' in which:
