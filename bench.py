@@ -227,10 +227,10 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        # stdout carries exactly one JSON line: keep NCCL's version banner
-        # (NCCL_DEBUG=VERSION) off it
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'
+        # stdout carries exactly one JSON line: at NCCL_DEBUG=VERSION (the
+        # setting of the GPU boxes) NCCL prints its version banner there
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+            del os.environ['NCCL_DEBUG']
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
     def barrier():
