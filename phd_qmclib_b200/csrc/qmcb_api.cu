@@ -110,6 +110,11 @@ struct qmcb_handle {
     double last_total_ms = 0.0, last_step_ms = 0.0;
     long long last_launches = 0;
 
+    // a block without estimators on one rank = one CUDA graph of
+    // 1 + 3 nts kernel nodes, rebuilt only when nts or the buffers change
+    cudaGraphExec_t block_graph = nullptr;
+    long long block_graph_nts = 0;
+
     // estimators (device)
     double *ssf_aux[2] = {nullptr, nullptr};    // [cap][M][3] ping-pong
     double *ssf_iter = nullptr;                 // [log_cap][M][3]
@@ -329,8 +334,16 @@ int launch_model_eval(qmcb_handle *h, const EvalArgs &a, bool want_ln,
     return QMCB_OK;
 }
 
+void drop_block_graph(qmcb_handle *h)
+{
+    if (h->block_graph) cudaGraphExecDestroy(h->block_graph);
+    h->block_graph = nullptr;
+    h->block_graph_nts = 0;
+}
+
 void free_dmc(qmcb_handle *h)
 {
+    drop_block_graph(h);
     DmcBufs &B = h->B;
     for (int i = 0; i < 2; ++i) {
         cudaFree(B.confs[i]); cudaFree(B.energy[i]); cudaFree(B.weight[i]);
@@ -369,6 +382,7 @@ void free_vmc(qmcb_handle *h)
 int alloc_dmc(qmcb_handle *h, const qmcb_dmc_params *p,
               long long slot_offset)
 {
+    const DmcConsts old_c = h->C;
     if (p->max_num_walkers < 1 || p->target_num_walkers < 1)
         FAIL(h, QMCB_ERR_INVALID, "max/target_num_walkers must be >= 1");
     long long cap = p->local_capacity > 0 ? p->local_capacity
@@ -448,6 +462,14 @@ int alloc_dmc(qmcb_handle *h, const qmcb_dmc_params *p,
     C.seed = p->rng_seed;
     C.slot_offset = slot_offset;
     C.energy_mode = p->energy_mode;
+    // the nodes of the block graph hold the constants by value (a
+    // reallocation has already dropped it in free_dmc)
+    if (old_c.dt != C.dt || old_c.sigma != C.sigma || old_c.z_min != C.z_min
+        || old_c.size != C.size || old_c.nwc_over_dt != C.nwc_over_dt
+        || old_c.target != C.target || old_c.seed != C.seed
+        || old_c.slot_offset != C.slot_offset
+        || old_c.energy_mode != C.energy_mode)
+        drop_block_graph(h);
     return QMCB_OK;
 }
 
@@ -591,6 +613,7 @@ int launch_density_step(qmcb_handle *h, long long step_idx)
 int ensure_log(qmcb_handle *h, long long nts)
 {
     if (nts <= h->log_cap) return QMCB_OK;
+    drop_block_graph(h);        // its nodes hold the old log pointers
     DmcLog &L = h->L;
     cudaFree(L.energy); cudaFree(L.weight); cudaFree(L.ref_energy);
     cudaFree(L.accum_energy); cudaFree(L.num_walkers);
@@ -919,6 +942,7 @@ int qmcb_set_model_params(qmcb_handle *h, const qmcb_model_params *params)
     // value), so no synchronisation is needed
     h->params = *params;
     h->M = M;
+    drop_block_graph(h);    // the step kernel's constants are node arguments
     return QMCB_OK;
 }
 
@@ -1163,7 +1187,6 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
     long long est_launches = 0;
     DmcBufs &B = h->B;
     DmcLog L = h->L;
-    L.block_step0 = h->step_host;
     const GroupGeom &g = h->geom;
     const int step_grid = (B.cap + g.G - 1) / g.G;
     if (h->profile_steps) {
@@ -1173,8 +1196,14 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
             h->step_ev.push_back(ev);
         }
     }
-    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
-    for (int64_t i = 0; i < nts; ++i) {
+    // A block on one rank with no estimators and no per-launch events is a
+    // fixed launch sequence with constant arguments: captured once into a
+    // CUDA graph and replayed (small populations are launch-bound: 3 kernels
+    // of a few microseconds each per time step).
+    static const bool no_graph = getenv("QMCB_NO_GRAPH") != nullptr;
+    const bool use_graph = !no_graph && !h->comm && !h->profile_steps
+                           && !do_ssf && !do_den;
+    auto enqueue_step = [&](int64_t i) -> int {
         branch_count_kernel<<<B.nblk, BR_THREADS, 0, h->stream>>>(B, h->C);
         branch_fill_kernel<<<B.nblk, BR_THREADS, 0, h->stream>>>(
             B, h->C, L, h->comm ? 0 : 1);
@@ -1194,6 +1223,40 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
             h->M, g, B, h->C);
         if (h->profile_steps)
             CUDA_TRY(h, cudaEventRecord(h->step_ev[2 * i + 1], h->stream));
+        return QMCB_OK;
+    };
+    if (use_graph && (!h->block_graph || h->block_graph_nts != nts)) {
+        drop_block_graph(h);
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(h, cudaStreamBeginCapture(h->stream,
+                                           cudaStreamCaptureModeThreadLocal));
+        dmc_block_begin_kernel<<<1, 32, 0, h->stream>>>(B);
+        for (int64_t i = 0; i < nts; ++i) enqueue_step(i);
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        if (ce != cudaSuccess || !graph) {
+            cudaGetLastError();
+            FAIL(h, QMCB_ERR_CUDA, std::string("graph capture of a DMC block "
+                                               "failed: ")
+                                       + cudaGetErrorString(ce));
+        }
+        ce = cudaGraphInstantiate(&h->block_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) {
+            h->block_graph = nullptr;
+            FAIL(h, QMCB_ERR_CUDA, std::string("cudaGraphInstantiate: ")
+                                       + cudaGetErrorString(ce));
+        }
+        h->block_graph_nts = nts;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    if (use_graph) {
+        CUDA_TRY(h, cudaGraphLaunch(h->block_graph, h->stream));
+    } else {
+        dmc_block_begin_kernel<<<1, 32, 0, h->stream>>>(B);
+    }
+    for (int64_t i = 0; i < nts && !use_graph; ++i) {
+        rc = enqueue_step(i);
+        if (rc) return rc;
         if (do_den) {
             rc = launch_density_step(h, i);
             if (rc) return rc;
@@ -1208,7 +1271,7 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     h->step_host += nts;
-    h->last_launches = (3 + (h->comm ? 2 : 0)) * nts + est_launches;
+    h->last_launches = 1 + (3 + (h->comm ? 2 : 0)) * nts + est_launches;
     if (density && do_den)
         CUDA_TRY(h, cudaMemcpyAsync(density, h->den_iter,
                                     nts * (size_t) NB * sizeof(double),

@@ -143,6 +143,7 @@ struct DmcCtl {
     double W_global;            // global live walkers of the last step
     unsigned int done_count;    // CTAs of branch_count_kernel that finished
     unsigned int done_fill;     // CTAs of branch_fill_kernel that finished
+    long long block_step0;      // `step` at the start of the block in flight
 };
 
 struct DmcBufs {
@@ -170,7 +171,6 @@ struct DmcConsts {
 struct DmcLog {
     double *energy, *weight, *ref_energy, *accum_energy;
     unsigned long long *num_walkers;
-    long long block_step0;      // ctl.step at block start
 };
 
 constexpr int BR_THREADS = 256;
@@ -306,7 +306,7 @@ __device__ __forceinline__ void dmc_finalize(const DmcBufs &B,
     ctl->last_weight = sW;
     ctl->last_accum = accum;
     ctl->W_global = sW;
-    long long i = t - L.block_step0;
+    long long i = t - ctl->block_step0;
     if (L.energy) {
         L.energy[i] = sE;
         L.weight[i] = sW;
@@ -379,6 +379,15 @@ branch_fill_kernel(DmcBufs B, DmcConsts C, DmcLog L, int finalize)
         B.ctl->red[1] = (double) B.ctl->W;
         if (finalize) dmc_finalize(B, C, L);
     }
+}
+
+// First launch of every block: the per-step log of the block starts at the
+// current step.  Keeping this on the device makes a block a launch sequence
+// whose arguments never change, i.e. one CUDA graph replayed per block.
+__global__ void dmc_block_begin_kernel(DmcBufs B)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        B.ctl->block_step0 = B.ctl->step;
 }
 
 // K7 on several ranks: after the all-reduce of ctl->red.

@@ -39,7 +39,8 @@ def vmc_c2(nch=100000, nop=50, ns=256, nblocks=3):
     return dict(config='C2 VMC N=50 1e5 chains M=50', blocks=out)
 
 
-def dmc(nop, nw, nts, v0, modes=0, bins=0, label='', nblocks=3, dt=1e-3):
+def dmc(nop, nw, nts, v0, modes=0, bins=0, label='', nblocks=3, dt=1e-3,
+        profile=True):
     spec = model.Spec(v0, 1, 2, nop, nop, 0.25 * nop)
     eng = engine.Engine(spec)
     cap = int(nw * 1.25)
@@ -48,7 +49,7 @@ def dmc(nop, nw, nts, v0, modes=0, bins=0, label='', nblocks=3, dt=1e-3):
                         density=(bins, True, nts) if bins else None)
     eng.dmc_init(dp, lattice_ini(nw, nop, 1))
     eng.dmc_run_block(nts)
-    eng.set_profiling(True)
+    eng.set_profiling(profile)     # per-launch events rule out the block graph
     out = []
     den = np.zeros((nts, bins)) if bins else None
     ssf = np.zeros((nts, modes, 3)) if modes else None
@@ -72,6 +73,8 @@ if __name__ == '__main__':
         print(json.dumps(vmc_c2(ns=16, nblocks=3)), flush=True)
     if 'c3' in which:
         print(json.dumps(dmc(50, 10000, 512, 5 * PI ** 2, label='C3 DMC N=50 1e4 walkers')), flush=True)
+    if 'c3g' in which:
+        print(json.dumps(dmc(50, 10000, 512, 5 * PI ** 2, profile=False, label='C3 DMC N=50 1e4 walkers, block graph')), flush=True)
     if 'c3big' in which:
         print(json.dumps(dmc(50, 250000, 128, 5 * PI ** 2, label='DMC N=50 2.5e5 walkers (population scaling of C3)')), flush=True)
     if 'c5' in which:

@@ -475,3 +475,39 @@ def test_too_many_particles_is_an_error(eng_mod):
     spec = model.Spec(10.0, 1, 2, 1028, 1028.0, 257.0)
     with pytest.raises(EngineError, match='too large'):
         eng_mod.Engine(spec)
+
+
+def test_block_graph_equals_stream_launches(eng_mod):
+    """A block without estimators replays a captured CUDA graph; with
+    per-launch events (set_profiling) the same block is launched kernel by
+    kernel.  Both must give the same bits, across a change of the block
+    length (graph rebuilt) and a restart (graph kept or rebuilt)."""
+    g = golden('model_lat_n50.npz')
+    p = g['params']
+    spec = (p[:12], p[12:19], p[19:])
+    rng = np.random.default_rng(31)
+    ini = np.zeros((70, 2, 50))
+    ini[:, 0] = rng.random((70, 50)) * 50
+    a, b = eng_mod.Engine(spec), eng_mod.Engine(spec)
+    dp = a.dmc_params(1e-3, 128, 70, 0.25, 21, 0.0, 50.0)
+    a.dmc_init(dp, ini)
+    b.dmc_init(dp, ini)
+    b.set_profiling(True)
+    for nts in (5, 5, 7, 1, 7):
+        x, y = a.dmc_run_block(nts), b.dmc_run_block(nts)
+        for k in x:
+            assert np.array_equal(x[k], y[k]), (nts, k)
+        assert a.last_block_stats()['launches'] == 1 + 3 * nts
+    nx = a.dmc_get_next()
+    dp2 = a.dmc_params(2e-3, 128, 70, 0.25, 21, 0.0, 50.0)   # new time step
+    for eng in (a, b):
+        eng.dmc_set_state(dp2, nx['confs'], nx['energy'], nx['weight'],
+                          nx['scalars'], slot_energy=nx['slot_energy'])
+    x, y = a.dmc_run_block(7), b.dmc_run_block(7)
+    for k in x:
+        assert np.array_equal(x[k], y[k]), k
+    sa, sb = a.dmc_get_state(), b.dmc_get_state()
+    for k in ('confs', 'energy', 'weight', 'mask', 'cloning_ref'):
+        assert np.array_equal(sa[k], sb[k]), k
+    a.close()
+    b.close()
