@@ -123,6 +123,11 @@ struct qmcb_handle {
     double *den_iter = nullptr;                 // [log_cap][B]
     double *est_partial = nullptr;              // [CS_BLOCKS][max(3M, B)]
     int *den_hi = nullptr;                      // highest slot count seen
+    // pure density without per-slot histograms (density_list_kernel)
+    bool den_lists_mode = false;
+    unsigned short *den_lists = nullptr;        // [steps][cap][N] bin indices
+    int *den_wrec = nullptr;                    // [steps] population recorded
+    long long den_lists_steps = 0;
     long long est_log_cap = 0;
 
     // correlated-sampling set of the wave-function optimiser (device)
@@ -357,8 +362,11 @@ void free_dmc(qmcb_handle *h)
     }
     cudaFree(h->ssf_iter); cudaFree(h->den_total); cudaFree(h->den_iter);
     cudaFree(h->est_partial); cudaFree(h->den_hi);
+    cudaFree(h->den_lists); cudaFree(h->den_wrec);
     h->ssf_iter = h->den_total = h->den_iter = h->est_partial = nullptr;
     h->den_hi = nullptr;
+    h->den_lists = nullptr; h->den_wrec = nullptr;
+    h->den_lists_steps = 0;
     h->est_log_cap = 0;
     cudaFree(h->L.energy); cudaFree(h->L.weight); cudaFree(h->L.ref_energy);
     cudaFree(h->L.accum_energy); cudaFree(h->L.num_walkers);
@@ -426,8 +434,13 @@ int alloc_dmc(qmcb_handle *h, const qmcb_dmc_params *p,
             for (int i = 0; i < 2; ++i)
                 CUDA_TRY(h, cudaMalloc(&h->ssf_aux[i],
                                        cap * M3 * sizeof(double)));
+        // pure mode: 16-bit bin lists instead of per-slot histograms
+        // (QMCB_DENSITY_HIST keeps the histogram path, for A/B tests)
+        h->den_lists_mode = NB && p->density_as_pure && NB <= 65536
+                            && !getenv("QMCB_DENSITY_HIST");
         if (NB) {
-            const int nh = p->density_as_pure ? 1 : 2;
+            const int nh = h->den_lists_mode ? 0
+                           : (p->density_as_pure ? 1 : 2);
             for (int i = 0; i < nh; ++i)
                 CUDA_TRY(h, cudaMalloc(&h->den_hist[i],
                                        cap * NB * sizeof(double)));
@@ -483,6 +496,17 @@ int ensure_est_log(qmcb_handle *h, long long nts)
     const size_t NB = (size_t) h->dp.density_num_bins;
     if (M3) CUDA_TRY(h, cudaMalloc(&h->ssf_iter, nts * M3 * sizeof(double)));
     if (NB) CUDA_TRY(h, cudaMalloc(&h->den_iter, nts * NB * sizeof(double)));
+    if (h->den_lists_mode) {
+        cudaFree(h->den_lists); cudaFree(h->den_wrec);
+        h->den_lists = nullptr; h->den_wrec = nullptr;
+        const long long steps = std::min<long long>(
+            nts, std::max<long long>(1, h->dp.density_pfw_nts));
+        CUDA_TRY(h, cudaMalloc(&h->den_lists,
+                               (size_t) steps * h->B.cap * h->M.nop
+                                   * sizeof(unsigned short)));
+        CUDA_TRY(h, cudaMalloc(&h->den_wrec, steps * sizeof(int)));
+        h->den_lists_steps = steps;
+    }
     h->est_log_cap = nts;
     return QMCB_OK;
 }
@@ -580,6 +604,35 @@ int launch_density_step(qmcb_handle *h, long long step_idx)
     const long long pfw = h->dp.density_pfw_nts;
     const int pbuf = pure ? 0 : (int) (step_idx & 1);
     int *W_dev = (int *) ((char *) B.ctl + offsetof(DmcCtl, W));
+    if (h->den_lists_mode) {
+        double *total = h->den_total, *corr = h->den_total + NB;
+        const long long stride = (long long) B.cap * N;
+        const long long nrec = std::min<long long>(
+            std::min(step_idx + 1, pfw), h->den_lists_steps);
+        if (step_idx < nrec) {
+            const double *confs =
+                B.confs[(int) ((h->step_host + step_idx) & 1)];
+            const size_t sm_bytes = (size_t) NB * sizeof(unsigned int);
+            const int use_smem = sm_bytes <= 160 * 1024;
+            if (use_smem && sm_bytes > 48 * 1024)
+                CUDA_TRY(h, cudaFuncSetAttribute(
+                                density_list_kernel,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) sm_bytes));
+            density_list_kernel<<<h->sm_count * (use_smem ? 2 : 8), 256,
+                                  use_smem ? sm_bytes : 0, h->stream>>>(
+                confs, B.ref, W_dev, N, NB, h->M.L / NB, B.cap,
+                h->den_lists + step_idx * stride, h->den_wrec + step_idx,
+                total, use_smem);
+        }
+        density_corr_kernel<<<dim3((unsigned) nrec, 16), 256, 0, h->stream>>>(
+            h->den_lists, h->den_wrec, W_dev, N, stride, corr);
+        const double div = (double) std::min(step_idx + 1, pfw);
+        density_out_kernel<<<(NB + 127) / 128, 128, 0, h->stream>>>(
+            total, corr, NB, 1.0 / div, h->den_iter + step_idx * NB);
+        CUDA_TRY(h, cudaGetLastError());
+        return QMCB_OK;
+    }
     double *hist = h->den_hist[pbuf];
     double *total = h->den_total + (size_t) pbuf * NB;
     if (!pure || step_idx < pfw) {

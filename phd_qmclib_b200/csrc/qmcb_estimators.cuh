@@ -292,6 +292,19 @@ __device__ __forceinline__ int py_floordiv_bin(double z, double b)
     return (int) fl;
 }
 
+// The same integer without fmod: the value above is the exact floor of the
+// real quotient z / b (fmod is exact, and the +0.5 test repairs the rounding
+// of the division).  k = floor(z * (1/b)) is off by at most one; the sign of
+// the fma residual z - k b is exact and says which way.
+__device__ __forceinline__ int floordiv_bin(double z, double b, double inv_b)
+{
+    double k = floor(z * inv_b);
+    const double r = fma(-k, b, z);
+    if (r < 0.0) k -= 1.0;
+    else if (r >= b) k += 1.0;
+    return (int) k;
+}
+
 // Per-slot histogram of the positions of the live walkers, plus the same
 // counts into the global running histogram `total` (all slots), which is
 // what lets the per-step sum over live slots be formed as
@@ -307,6 +320,7 @@ density_hist_kernel(const double *confs, const int *ref, const int *W_dev,
 {
     extern __shared__ unsigned int dens_smem[];
     const long long W = *W_dev;
+    const double inv_bin = 1.0 / bin_size;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(hi_dev, (int) W);
     if (use_smem) {
         for (int b = threadIdx.x; b < nbins; b += blockDim.x)
@@ -319,7 +333,7 @@ density_hist_kernel(const double *confs, const int *ref, const int *W_dev,
         long long s = e / N;
         int i = (int) (e - s * N);
         double z = confs[(long long) ref[s] * 2 * N + i];
-        int b = py_floordiv_bin(z, bin_size);
+        int b = floordiv_bin(z, bin_size, inv_bin);
         b = b < 0 ? 0 : (b >= nbins ? nbins - 1 : b);     // quirk Q5: clamp
         atomicAdd(hist + s * nbins + b, 1.0);
         if (use_smem) atomicAdd(dens_smem + b, 1u);
@@ -334,6 +348,79 @@ density_hist_kernel(const double *confs, const int *ref, const int *W_dev,
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Pure density estimator without per-slot histograms.  In pure mode the
+// reference ignores the genealogy (quirk Q2): slot s simply accumulates the
+// counts of whatever walker occupies it, and step t sums the rows of the
+// slots that are live at t.  Hence
+//   out(t) = [ sum over recorded steps t' <= t of ALL counts of t' ]
+//            - [ counts of step t' in the slots W_t <= s < W_t' ]   (t' < t)
+// The first term is one running histogram; the second touches only the few
+// slots by which the population has shrunk since t'.  Instead of 8 B x bins
+// per slot updated with N scattered read-modify-writes per walker and step,
+// a step writes N 16-bit bin indices per walker, coalesced.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+density_list_kernel(const double *confs, const int *ref, const int *W_dev,
+                    int N, int nbins, double bin_size, int cap,
+                    unsigned short *lists,      // [cap][N] of this step
+                    int *W_rec,                 // population of this step
+                    double *total, int use_smem)
+{
+    extern __shared__ unsigned int dens_smem[];
+    const long long W = *W_dev;
+    const double inv_bin = 1.0 / bin_size;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *W_rec = (int) W;
+    if (use_smem) {
+        for (int b = threadIdx.x; b < nbins; b += blockDim.x)
+            dens_smem[b] = 0u;
+        __syncthreads();
+    }
+    const long long n = W * N;
+    for (long long e = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+         e < n; e += (long long) gridDim.x * blockDim.x) {
+        long long s = e / N;
+        int i = (int) (e - s * N);
+        double z = confs[(long long) ref[s] * 2 * N + i];
+        int b = floordiv_bin(z, bin_size, inv_bin);
+        b = b < 0 ? 0 : (b >= nbins ? nbins - 1 : b);     // quirk Q5: clamp
+        lists[e] = (unsigned short) b;
+        if (use_smem) atomicAdd(dens_smem + b, 1u);
+        else atomicAdd(total + b, 1.0);
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
+            unsigned int c = dens_smem[b];
+            if (c) atomicAdd(total + b, (double) c);
+        }
+    }
+}
+
+// CTA t': counts of recorded step t' in the slots that have died since
+// (exact integer-valued atomics: order-independent).
+__global__ void __launch_bounds__(256)
+density_corr_kernel(const unsigned short *lists, const int *W_rec,
+                    const int *W_dev, int N, long long step_stride,
+                    double *corr)
+{
+    const long long Wt = *W_dev, Wp = W_rec[blockIdx.x];
+    if (Wp <= Wt) return;
+    const unsigned short *l = lists + blockIdx.x * step_stride;
+    for (long long e = Wt * N + blockIdx.y * blockDim.x + threadIdx.x;
+         e < Wp * N; e += (long long) gridDim.y * blockDim.x)
+        atomicAdd(corr + l[e], 1.0);
+}
+
+__global__ void density_out_kernel(const double *total, double *corr,
+                                   int nbins, double scale, double *out)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbins) return;
+    out[b] = (total[b] - corr[b]) * scale;
+    corr[b] = 0.0;
+}
 
 // ---------------------------------------------------------------------------
 // One-body density matrix  g1(sz) = (1/N) sum_i Psi(.., z_i + sz, ..) / Psi

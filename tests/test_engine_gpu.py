@@ -511,3 +511,44 @@ def test_block_graph_equals_stream_launches(eng_mod):
         assert np.array_equal(sa[k], sb[k]), k
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize('pure', [True, False])
+def test_density_bin_edges_vs_oracle(eng_mod, oracle, pure):
+    """Positions exactly on bin edges and one ulp to either side, with a bin
+    width that is not a binary fraction: the engine's floor division (an fma
+    residual instead of the reference's fmod-based Python `//`) must land in
+    the same bin as the oracle, which restates the reference op for op."""
+    g = golden('model_frac_n21.npz')
+    p = g['params']
+    nop, size = int(p[3]), float(p[4])
+    bins, n_ini, wmax, nts = 37, 40, 64, 3
+    width = size / bins
+    rng = np.random.default_rng(12)
+    k = rng.integers(0, bins, size=(n_ini, nop)).astype(np.float64)
+    z = k * width
+    z[1::3] = np.nextafter(z[1::3], np.inf)
+    z[2::3] = np.nextafter(z[2::3], -np.inf)
+    z = np.clip(z, 0.0, np.nextafter(size, 0.0))
+    # keep the particles of a walker apart (coincident particles are not
+    # what this test is about)
+    z += 1e-3 * width * np.argsort(rng.random((n_ini, nop)), axis=1) \
+        * (rng.random((n_ini, 1)) < 0.5)
+    ini = np.zeros((n_ini, 2, nop))
+    ini[:, 0] = z
+    st = oracle.DMCState(p, ini, wmax)
+    den = dict(num=bins, pure=pure, pfw=nts, iter=np.zeros((nts, bins)),
+               aux=np.zeros((2, wmax, bins)))
+    eng = eng_mod.Engine((p[:12], p[12:19], p[19:]))
+    dp = eng.dmc_params(1e-4, wmax, n_ini, 0.25, 5, 0.0, size,
+                        density=(bins, pure, nts))
+    eng.dmc_init(dp, ini)
+    a = st.run_block(5, 1e-4, n_ini, 0.25, nts, 0.0, size, eval_est=True,
+                     density=den)
+    e_den = np.zeros((nts, bins))
+    b = eng.dmc_run_block(nts, eval_estimators=True, density=e_den)
+    assert np.array_equal(a['num_walkers'], b['num_walkers'])
+    # step 0 histograms the initial positions themselves: integer counts
+    assert np.array_equal(e_den[0], den['iter'][0])
+    assert np.allclose(e_den, den['iter'], rtol=1e-13, atol=1e-13)
+    eng.close()
