@@ -280,22 +280,13 @@ __global__ void colsum_final_kernel(const double *partial, int nblk, int ncol,
     out[c] = v * scale;
 }
 
-// Python float floor division z // b (numba lowers `//` to this), as an
-// integer bin index (mrbp_qmc/dmc.py:530,544).
-__device__ __forceinline__ int py_floordiv_bin(double z, double b)
-{
-    double mod = fmod(z, b);
-    double div = (z - mod) / b;
-    if (mod != 0.0 && ((b < 0.0) != (mod < 0.0))) div -= 1.0;
-    double fl = floor(div);
-    if (div - fl > 0.5) fl += 1.0;
-    return (int) fl;
-}
-
-// The same integer without fmod: the value above is the exact floor of the
-// real quotient z / b (fmod is exact, and the +0.5 test repairs the rounding
-// of the division).  k = floor(z * (1/b)) is off by at most one; the sign of
-// the fma residual z - k b is exact and says which way.
+// Bin index of a position: Python float floor division z // b (numba lowers
+// `//` to: mod = fmod(z, b); div = (z - mod) / b; floor(div), rounded up when
+// div - floor(div) > 0.5; mrbp_qmc/dmc.py:530,544).  For b > 0 that value is
+// the exact floor of the real quotient z / b (fmod is exact and the 0.5 test
+// repairs the rounding of the division), which needs no fmod:
+// k = floor(z * (1/b)) is off by at most one, and the sign of the fma
+// residual z - k b is exact and says which way.
 __device__ __forceinline__ int floordiv_bin(double z, double b, double inv_b)
 {
     double k = floor(z * inv_b);
