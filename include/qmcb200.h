@@ -240,6 +240,21 @@ QMCB_API int qmcb_dmc_get_next(qmcb_handle *h, double *confs, double *energy,
                                double *weight, double *slot_energy,
                                qmcb_state_scalars *scalars);
 
+/* On-the-fly reblocking of the per-step series on the device, so that long
+ * runs need not ship the series themselves.  Replaces, for the five series of
+ * PropsData (energy, weight, num_walkers, ref_energy, accum_energy; rows of
+ * the tables in that order), stats.reblock._on_the_fly_obj_create
+ * (stats/reblock.py:525-604) applied to each block's series and
+ * on_the_fly_obj_data_update (:927-948) over the blocks run since the reset:
+ * for order k = 0..max_order, the sum and the sum of squares of the means of
+ * blocks of 2^k consecutive steps and their number (fields MEANS, MEANS_SQR,
+ * NUM_BLOCKS of otf_data_dtype, :436-441; BLOCK_SIZE = 2^k).  A block of nts
+ * steps feeds the orders up to floor(log2 nts).  max_order < 0 switches the
+ * accumulators off.  Tables are [5][max_order + 1], host, each may be NULL. */
+QMCB_API int qmcb_dmc_reblock_reset(qmcb_handle *h, int32_t max_order);
+QMCB_API int qmcb_dmc_reblock_get(qmcb_handle *h, double *means_sum,
+                                  double *means_sqr_sum, int64_t *num_blocks);
+
 /* on != 0: bracket every step-kernel launch with CUDA events so that
  * qmcb_last_block_stats can report the step kernel's own device time. */
 QMCB_API int qmcb_set_profiling(qmcb_handle *h, int32_t on);

@@ -430,6 +430,43 @@ def gen_vmc_stat(mrbp, name, kwargs, *, move_spread, ns, nblocks, burn, seed,
           f'acc = {np.mean(acc):.4f}')
 
 
+def gen_reblock(rng):
+    """On-the-fly reblocking tables of the live reference
+    (stats/reblock.py: on_the_fly_obj_create, on_the_fly_obj_data_update and
+    the OTFObject statistics derived from them) for correlated series whose
+    lengths are and are not powers of two."""
+    import warnings
+    from phd_qmclib.stats import reblock
+    out = {}
+    for tag, n, ncols in (('a', 100, 3), ('b', 64, 2), ('c', 12, 5),
+                          ('d', 1, 1)):
+        x = np.cumsum(rng.standard_normal((n, ncols)), axis=0) * 0.1 \
+            + 10 * rng.random(ncols)
+        otf = reblock.on_the_fly_obj_create(x)
+        out[f'{tag}_series'] = x
+        for f in otf.dtype.names:
+            out[f'{tag}_{f}'] = otf[f]
+    # accumulation over consecutive "blocks" and the statistics the
+    # reference derives from an accumulated table
+    blocks = [np.cumsum(rng.standard_normal(48)) * 0.05 + 3 for _ in range(5)]
+    acc = reblock.on_the_fly_obj_create(blocks[0])
+    for b in blocks[1:]:
+        reblock.on_the_fly_obj_data_update(
+            acc, reblock.on_the_fly_obj_create(b))
+    out['acc_blocks'] = np.array(blocks)
+    for f in acc.dtype.names:
+        out[f'acc_{f}'] = acc[f]
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        obj = reblock.OTFObject(acc)
+        out['acc_mean'] = obj.mean
+        out['acc_errors'] = obj.errors
+        out['acc_mean_eff_error'] = obj.mean_eff_error
+    np.savez_compressed(os.path.join(GOLDEN, 'reblock_otf.npz'), **out)
+    print('reblock_otf: mean', float(out['acc_mean']),
+          'eff error', float(out['acc_mean_eff_error']))
+
+
 def gen_cswf(mrbp, name, kwargs, rng, *, nconf, cutoffs):
     """Correlated-sampling objective of the wave-function optimiser
     (mrbp_qmc/model.py:817-942) on a fixed configuration set: ln|Psi| and
@@ -472,13 +509,15 @@ def gen_cswf(mrbp, name, kwargs, rng, *, nconf, cutoffs):
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     which = set(sys.argv[1:]) or {'model', 'step', 'branch', 'blocks', 'vmc',
-                                  'stat', 'cswf'}
+                                  'stat', 'cswf', 'reblock'}
     mrbp = refshim.load()
     from phd_qmclib.mrbp_qmc import dmc, model, vmc  # noqa: F401
     draw_uniform, draw_dmc = numba_draws()
     if 'model' in which:
         for i, (name, kw) in enumerate(SPECS.items()):
             gen_model(mrbp, name, kw, np.random.default_rng(100 + i))
+    if 'reblock' in which:
+        gen_reblock(np.random.default_rng(700))
     if 'cswf' in which:
         gen_cswf(mrbp, 'll_n16', SPECS['ll_n16'], np.random.default_rng(600),
                  nconf=96, cutoffs=[0.05, 1.0, 2.5, 4.0, 6.0, 7.92])

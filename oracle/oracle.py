@@ -167,6 +167,58 @@ def weighed_variance(wf_abs_log_set, ini_wf_abs_log_set, energy_set):
     return e_diff.sum() / weight_sum, ref_energy
 
 
+OTF_DTYPE = np.dtype([('BLOCK_SIZE', np.int64), ('MEANS', np.float64),
+                      ('MEANS_SQR', np.float64), ('NUM_BLOCKS', np.int64)])
+
+
+def otf_create(source_data):
+    """On-the-fly reblocking tables of a series [n] or [n, ncols]:
+    stats/reblock.py:447-457 (order), :508-522 (init), :525-604 (the loop),
+    statement by statement.  Returns a structured array [ncols, order + 1]
+    ([order + 1] for a 1-d series) with the reference's otf_data_dtype."""
+    import math
+    src = np.asarray(source_data, dtype=np.float64)
+    one_d = src.ndim == 1
+    if one_d:
+        src = src[:, None]
+    n, ncols = src.shape
+    max_order = int(math.floor(math.log(n) / math.log(2)))
+    otf = np.zeros((ncols, max_order + 1), dtype=OTF_DTYPE)
+    for order in range(max_order + 1):
+        otf['BLOCK_SIZE'][:, order] = 1 << order
+    means = np.zeros((ncols, max_order + 1, 2))
+    for index in range(n):
+        order, block_size, next_block_size = 0, 1, 2
+        mean_index = index % 2
+        for nc in range(ncols):
+            v = src[index, nc]
+            otf['MEANS'][nc, 0] += v
+            otf['MEANS_SQR'][nc, 0] += v * v        # numba lowers x ** 2 to x * x
+            means[nc, 0, mean_index] = v
+            otf['NUM_BLOCKS'][nc, 0] += 1
+        while order < max_order and not (index + 1) % next_block_size:
+            order += 1
+            block_size <<= 1
+            block_index = (index + 1) // block_size - 1
+            mean_index = block_index % 2
+            for nc in range(ncols):
+                m = means[nc, order - 1].mean()
+                otf['MEANS'][nc, order] += m
+                otf['MEANS_SQR'][nc, order] += m * m
+                means[nc, order, mean_index] = m
+                otf['NUM_BLOCKS'][nc, order] += 1
+            next_block_size = block_size << 1
+    return otf[0] if one_d else otf
+
+
+def otf_update(obj_data, ext_obj_data):
+    """stats/reblock.py:927-948: accumulate a compatible table in place."""
+    assert np.all(obj_data['BLOCK_SIZE'] == ext_obj_data['BLOCK_SIZE'])
+    obj_data['MEANS'] += ext_obj_data['MEANS']
+    obj_data['MEANS_SQR'] += ext_obj_data['MEANS_SQR']
+    obj_data['NUM_BLOCKS'] += ext_obj_data['NUM_BLOCKS']
+
+
 def one_body_density(params, confs, offsets):
     """confs [B,2,N], offsets [S] -> [B,S]."""
     p = _params(params)

@@ -24,7 +24,7 @@ SYMBOLS = [
     'qmcb_host_alloc', 'qmcb_host_free', 'qmcb_rebalance_plan',
     'qmcb_one_body_density', 'qmcb_one_body_density_device',
     'qmcb_fourier_density_k', 'qmcb_set_model_params', 'qmcb_cs_load',
-    'qmcb_cs_variance',
+    'qmcb_cs_variance', 'qmcb_dmc_reblock_reset', 'qmcb_dmc_reblock_get',
 ]
 
 
@@ -108,6 +108,8 @@ def load():
     L.qmcb_dmc_get_next.argtypes = [vp, vp, vp, vp, vp,
                                     C.POINTER(StateScalars)]
     L.qmcb_set_profiling.argtypes = [vp, i32]
+    L.qmcb_dmc_reblock_reset.argtypes = [vp, i32]
+    L.qmcb_dmc_reblock_get.argtypes = [vp, vp, vp, vp]
     L.qmcb_last_block_stats.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl),
                                         C.POINTER(i64)]
     L.qmcb_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(dbl), C.POINTER(dbl)]

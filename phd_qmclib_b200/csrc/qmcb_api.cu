@@ -115,6 +115,9 @@ struct qmcb_handle {
     cudaGraphExec_t block_graph = nullptr;
     long long block_graph_nts = 0;
 
+    // on-the-fly reblocking tables of the per-step series (device)
+    ReblockTables rb{};
+
     // estimators (device)
     double *ssf_aux[2] = {nullptr, nullptr};    // [cap][M][3] ping-pong
     double *ssf_iter = nullptr;                 // [log_cap][M][3]
@@ -785,6 +788,7 @@ void qmcb_destroy(qmcb_handle *h)
     free_vmc(h);
     cudaFree(h->d_scratch);
     cudaFree(h->d_counts);
+    cudaFree(h->rb.sum); cudaFree(h->rb.sqr); cudaFree(h->rb.nblk);
     cudaFree(h->cs_confs); cudaFree(h->cs_ln0); cudaFree(h->cs_work);
     if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
     for (auto ev : h->step_ev) cudaEventDestroy(ev);
@@ -1321,6 +1325,12 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
             est_launches += 3;
         }
     }
+    if (h->rb.K > 0) {
+        // same expression as on_the_fly_obj_data_order (stats/reblock.py:447)
+        const int order = (int) std::floor(std::log((double) nts)
+                                           / std::log(2.0));
+        reblock_series_kernel<<<1, 32, 0, h->stream>>>(L, nts, order, h->rb);
+    }
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     h->step_host += nts;
@@ -1366,6 +1376,53 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
         }
         h->last_step_ms = acc;
     }
+    return QMCB_OK;
+}
+
+int qmcb_dmc_reblock_reset(qmcb_handle *h, int32_t max_order)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (max_order >= RB_MAX_ORDERS)
+        FAIL(h, QMCB_ERR_INVALID, "max_order too large");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->rb.sum); cudaFree(h->rb.sqr); cudaFree(h->rb.nblk);
+    h->rb = ReblockTables{};
+    if (max_order < 0) return QMCB_OK;          // switched off
+    const int K = max_order + 1;
+    const size_t n = (size_t) RB_COLS * K;
+    CUDA_TRY(h, cudaMalloc(&h->rb.sum, n * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&h->rb.sqr, n * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&h->rb.nblk, n * sizeof(long long)));
+    CUDA_TRY(h, cudaMemsetAsync(h->rb.sum, 0, n * sizeof(double), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->rb.sqr, 0, n * sizeof(double), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->rb.nblk, 0, n * sizeof(long long),
+                                h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->rb.K = K;
+    return QMCB_OK;
+}
+
+int qmcb_dmc_reblock_get(qmcb_handle *h, double *means_sum,
+                         double *means_sqr_sum, int64_t *num_blocks)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (h->rb.K < 1)
+        FAIL(h, QMCB_ERR_STATE, "qmcb_dmc_reblock_reset not called");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = (size_t) RB_COLS * h->rb.K;
+    if (means_sum)
+        CUDA_TRY(h, cudaMemcpyAsync(means_sum, h->rb.sum, n * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (means_sqr_sum)
+        CUDA_TRY(h, cudaMemcpyAsync(means_sqr_sum, h->rb.sqr,
+                                    n * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (num_blocks)
+        CUDA_TRY(h, cudaMemcpyAsync(num_blocks, h->rb.nblk,
+                                    n * sizeof(long long),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return QMCB_OK;
 }
 

@@ -390,6 +390,67 @@ __global__ void dmc_block_begin_kernel(DmcBufs B)
         B.ctl->block_step0 = B.ctl->step;
 }
 
+// On-the-fly reblocking of the five per-step series of a block
+// (stats/reblock.py:525-604 `_on_the_fly_obj_create`, accumulated over the
+// blocks like `on_the_fly_obj_data_update` :927-948): for every order k the
+// sum and the sum of squares of the means of blocks of 2^k consecutive steps,
+// built pairwise from the two means of order k-1 exactly as the reference
+// does, so the tables are bit-identical to reblocking the shipped series.
+// Thread c = series c (energy, weight, num_walkers, ref_energy, accum_energy).
+constexpr int RB_COLS = 5;
+constexpr int RB_MAX_ORDERS = 40;
+
+struct ReblockTables {
+    double *sum, *sqr;              // [RB_COLS][K]
+    long long *nblk;                // [RB_COLS][K]
+    int K;                          // orders kept: 0 .. K-1
+};
+
+__global__ void reblock_series_kernel(DmcLog L, long long nts,
+                                      int block_max_order, ReblockTables T)
+{
+    const int c = threadIdx.x;
+    if (blockIdx.x != 0 || c >= RB_COLS) return;
+    const int kmax = block_max_order < T.K - 1 ? block_max_order : T.K - 1;
+    // the table of THIS block first (on_the_fly_obj_create), added to the
+    // running table afterwards (on_the_fly_obj_data_update): the same
+    // association of the sums as the reference's
+    double means[RB_MAX_ORDERS][2], sum[RB_MAX_ORDERS], sqr[RB_MAX_ORDERS];
+    long long nb[RB_MAX_ORDERS];
+    for (int k = 0; k <= kmax; ++k) { sum[k] = 0.0; sqr[k] = 0.0; nb[k] = 0; }
+    for (long long idx = 0; idx < nts; ++idx) {
+        double v;
+        switch (c) {
+        case 0: v = L.energy[idx]; break;
+        case 1: v = L.weight[idx]; break;
+        case 2: v = (double) L.num_walkers[idx]; break;
+        case 3: v = L.ref_energy[idx]; break;
+        default: v = L.accum_energy[idx]; break;
+        }
+        means[0][idx & 1] = v;
+        sum[0] = __dadd_rn(sum[0], v);
+        sqr[0] = __dadd_rn(sqr[0], __dmul_rn(v, v));
+        nb[0] += 1;
+        long long bs = 1;
+        for (int k = 1; k <= kmax; ++k) {
+            bs <<= 1;
+            if ((idx + 1) % bs) break;
+            const long long bidx = (idx + 1) / bs - 1;
+            const double m = __ddiv_rn(
+                __dadd_rn(means[k - 1][0], means[k - 1][1]), 2.0);
+            means[k][bidx & 1] = m;
+            sum[k] = __dadd_rn(sum[k], m);
+            sqr[k] = __dadd_rn(sqr[k], __dmul_rn(m, m));
+            nb[k] += 1;
+        }
+    }
+    for (int k = 0; k <= kmax; ++k) {
+        T.sum[c * T.K + k] = __dadd_rn(T.sum[c * T.K + k], sum[k]);
+        T.sqr[c * T.K + k] = __dadd_rn(T.sqr[c * T.K + k], sqr[k]);
+        T.nblk[c * T.K + k] += nb[k];
+    }
+}
+
 // K7 on several ranks: after the all-reduce of ctl->red.
 __global__ void dmc_finalize_kernel(DmcBufs B, DmcConsts C, DmcLog L)
 {

@@ -232,7 +232,9 @@ class Sampling:
     stale-slot energy in the branching weight; 1 = the parent's
     energy), ``eager_last_state`` (copy the State back after every block),
     ``dist`` (an initialised ``torch.distributed``-like module: one process
-    per GPU, the walkers sharded over the ranks).
+    per GPU, the walkers sharded over the ranks), ``reblock_max_order`` (keep
+    on-the-fly reblocking tables of the per-step series on the device, read
+    with :meth:`otf_reblock_data`).
 
     With ``dist``: ``max_num_walkers`` / ``target_num_walkers`` stay GLOBAL;
     rank r owns the r-th contiguous slab of the ensemble in
@@ -258,6 +260,7 @@ class Sampling:
     energy_mode: int = 0
     eager_last_state: bool = False
     dist: t.Any = None
+    reblock_max_order: t.Optional[int] = None
     _cache: dict = field(default_factory=dict, init=False, repr=False,
                          compare=False)
 
@@ -438,6 +441,20 @@ class Sampling:
             np.asarray(props.energy)[:n], np.asarray(props.weight)[:n], sc,
             slot_energy=np.asarray(props.energy, dtype=np.float64),
             global_slot_offset=self.rank * self.local_capacity)
+        if self.reblock_max_order is not None:
+            self.engine.dmc_reblock_reset(self.reblock_max_order)
+
+    def otf_reblock_data(self) -> t.Dict[str, np.ndarray]:
+        """Accumulated on-the-fly reblocking tables of the per-step series
+        (energy, weight, num_walkers, ref_energy, accum_energy) of every
+        block run since the iterator started, in the reference's
+        ``otf_data_dtype``: ``stats.reblock.OTFObject(table)`` gives means,
+        errors per block size and the optimal block size without the series
+        having left the GPU (reference ``stats/reblock.py:525-604, 652-757``).
+        Needs ``reblock_max_order``."""
+        if self.reblock_max_order is None:
+            raise TypeError('reblock_max_order has not been specified')
+        return self.engine.dmc_reblock_get()
 
     def _fetch_state(self, stamp=None) -> State:
         eng = self.engine

@@ -385,6 +385,40 @@ class Engine:
         self._check(rc, 'qmcb_dmc_rebalance')
         return moved.value
 
+    #: dtype of the reference's reblocking tables (stats/reblock.py:436-441)
+    OTF_DTYPE = np.dtype([('BLOCK_SIZE', np.int64), ('MEANS', np.float64),
+                          ('MEANS_SQR', np.float64),
+                          ('NUM_BLOCKS', np.int64)])
+    REBLOCK_SERIES = ('energy', 'weight', 'num_walkers', 'ref_energy',
+                      'accum_energy')
+
+    def dmc_reblock_reset(self, max_order):
+        """Start (``max_order`` >= 0) or stop (None / < 0) the on-device
+        reblocking accumulators of the per-step series."""
+        mo = -1 if max_order is None else int(max_order)
+        rc = self._L.qmcb_dmc_reblock_reset(self._h, mo)
+        self._check(rc, 'qmcb_dmc_reblock_reset')
+        self._rb_orders = mo + 1
+
+    def dmc_reblock_get(self):
+        """dict series name -> structured array (orders,) with the fields of
+        the reference's ``otf_data_dtype``: feed it to
+        ``stats.reblock.OTFObject`` as is."""
+        K = getattr(self, '_rb_orders', 0)
+        sums, sqr = np.zeros((5, K)), np.zeros((5, K))
+        nblk = np.zeros((5, K), dtype=np.int64)
+        rc = self._L.qmcb_dmc_reblock_get(self._h, ptr(sums), ptr(sqr),
+                                          ptr(nblk))
+        self._check(rc, 'qmcb_dmc_reblock_get')
+        out = {}
+        for c, name in enumerate(self.REBLOCK_SERIES):
+            t_ = np.zeros(K, dtype=self.OTF_DTYPE)
+            t_['BLOCK_SIZE'] = 1 << np.arange(K)
+            t_['MEANS'], t_['MEANS_SQR'] = sums[c], sqr[c]
+            t_['NUM_BLOCKS'] = nblk[c]
+            out[name] = t_
+        return out
+
     def set_profiling(self, on=True):
         self._check(self._L.qmcb_set_profiling(self._h, int(on)),
                     'qmcb_set_profiling')

@@ -552,3 +552,45 @@ def test_density_bin_edges_vs_oracle(eng_mod, oracle, pure):
     assert np.array_equal(e_den[0], den['iter'][0])
     assert np.allclose(e_den, den['iter'], rtol=1e-13, atol=1e-13)
     eng.close()
+
+
+def test_on_device_reblocking_vs_oracle(eng_mod, oracle):
+    """qmcb_dmc_reblock_*: the accumulated on-the-fly reblocking tables of
+    the five per-step series equal the reference's on_the_fly_obj_create of
+    each shipped block series, accumulated with on_the_fly_obj_data_update
+    -- bit for bit; block lengths 12 and 16 (orders 3 and 4)."""
+    g = golden('model_ll_n16.npz')
+    p = g['params']
+    rng = np.random.default_rng(2)
+    ini = np.zeros((200, 2, 16))
+    ini[:, 0] = rng.random((200, 16)) * 16
+    eng = eng_mod.Engine((p[:12], p[12:19], p[19:]))
+    dp = eng.dmc_params(2e-3, 320, 200, 0.125, 3, 0.0, 16.0)
+    eng.dmc_init(dp, ini)
+    eng.dmc_run_block(8)                    # before the reset: not counted
+    eng.dmc_reblock_reset(4)
+    want = {}
+    for nts in (12, 16, 12, 1):
+        blk = eng.dmc_run_block(nts)
+        for name in eng.REBLOCK_SERIES:
+            t_ = oracle.otf_create(blk[name].astype(np.float64))
+            full = np.zeros(5, dtype=oracle.OTF_DTYPE)
+            full['BLOCK_SIZE'] = 1 << np.arange(5)
+            k = min(len(t_), 5)
+            for f in ('MEANS', 'MEANS_SQR', 'NUM_BLOCKS'):
+                full[f][:k] = t_[f][:k]
+            if name in want:
+                oracle.otf_update(want[name], full)
+            else:
+                want[name] = full
+    got = eng.dmc_reblock_get()
+    for name in eng.REBLOCK_SERIES:
+        assert got[name].dtype == oracle.OTF_DTYPE
+        for f in oracle.OTF_DTYPE.names:
+            assert np.array_equal(got[name][f], want[name][f]), (name, f)
+    assert got['energy']['NUM_BLOCKS'].tolist() == [41, 20, 10, 4, 1]
+    eng.dmc_reblock_reset(None)             # switched off again
+    eng.dmc_run_block(4)
+    with pytest.raises(Exception):
+        eng.dmc_reblock_get()
+    eng.close()

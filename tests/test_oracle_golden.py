@@ -155,3 +155,27 @@ def test_vmc_blocks(oracle, name):
             float(g['it_accept_rate'][b]), abs=1e-15)
     assert np.allclose(cur[0, 0], g['last_conf'][0], rtol=0, atol=1e-12)
     assert nop == int(g['params'][3])
+
+
+def test_otf_reblocking(oracle):
+    """The restatement of stats/reblock.py's on-the-fly reblocking against
+    tables made by the live reference: bit for bit (same operations in the
+    same order), for lengths that are and are not powers of two."""
+    g = golden('reblock_otf.npz')
+    for tag in 'abcd':
+        otf = oracle.otf_create(g[f'{tag}_series'])
+        for f in otf.dtype.names:
+            assert np.array_equal(otf[f], g[f'{tag}_{f}']), (tag, f)
+    blocks = g['acc_blocks']
+    acc = oracle.otf_create(blocks[0])
+    for b in blocks[1:]:
+        oracle.otf_update(acc, oracle.otf_create(b))
+    for f in acc.dtype.names:
+        assert np.array_equal(acc[f], g[f'acc_{f}']), f
+    # what the reference derives from such a table (OTFObject.mean / errors)
+    nb = acc['NUM_BLOCKS'][acc['NUM_BLOCKS'] >= 2]
+    k = len(nb)
+    means = acc['MEANS'][:k] / nb
+    var = nb * (acc['MEANS_SQR'][:k] / nb - means ** 2) / (nb - 1)
+    assert means[0] == g['acc_mean']
+    assert np.allclose(np.sqrt(var / nb), g['acc_errors'], rtol=1e-13)
