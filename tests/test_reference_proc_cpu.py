@@ -191,6 +191,84 @@ def test_reference_dmc_proc_drives_b200_sampling(ref, doubled):
     assert nw_last.shape == (4,)
 
 
+def test_reference_hdf5_handler_round_trip(ref, doubled, monkeypatch, tmp_path):
+    """the result of a B200-backed procedure goes through the
+    reference's UNCHANGED HDF5FileHandler (qmc_exec/io.py:76-132,
+    qmc_exec/dmc/io.py:35-98, qmc_exec/data/dmc.py hdf5_export) into the
+    reference's file layout and back into a ProcResult that restarts.  h5py
+    is not in this image: tests/_fake_h5py.py stands in for the dozen calls
+    the handler makes."""
+    import attr
+    import _fake_h5py
+    from phd_qmclib.mrbp_qmc import Spec, dmc_exec
+    from phd_qmclib.qmc_exec import io as io_base
+    from phd_qmclib.qmc_exec.dmc import io as dmc_io
+    from phd_qmclib.qmc_exec.data import dmc as data_dmc
+    for mod in (io_base, dmc_io, data_dmc):
+        monkeypatch.setattr(mod, 'h5py', _fake_h5py, raising=False)
+    b200_dmc, _ = doubled
+
+    @attr.s(auto_attribs=True, frozen=True)
+    class B200Proc(dmc_exec.Proc):
+        @functools.cached_property
+        def sampling(self):
+            nts = self.num_time_steps_block
+            return b200_dmc.Sampling(
+                self.model_spec, self.time_step, self.max_num_walkers,
+                self.target_num_walkers, self.num_walkers_control_factor,
+                self.rng_seed,
+                density_est_spec=b200_dmc.DensityEstSpec(
+                    self.density_spec.num_bins,
+                    self.density_spec.as_pure_est, nts),
+                ssf_est_spec=b200_dmc.SSFEstSpec(
+                    self.ssf_spec.num_modes, self.ssf_spec.as_pure_est, nts))
+
+    spec = Spec(lattice_depth=5 * np.pi ** 2, lattice_ratio=1,
+                interaction_strength=2, boson_number=8, supercell_size=8,
+                tbf_contact_cutoff=2)
+    proc = B200Proc(spec, 1e-3, 48, 32, rng_seed=5, num_blocks=3,
+                    num_time_steps_block=8, burn_in_blocks=1,
+                    density_spec=dmc_exec.DensityEstSpec(num_bins=16),
+                    ssf_spec=dmc_exec.SSFEstSpec(num_modes=4))
+    np.random.seed(3)
+    result = proc.exec(dmc_exec.ProcInput.from_model_sys_conf_spec(
+        dmc_exec.ModelSysConfSpec(dist_type='RANDOM'), proc))
+    handler = dmc_exec.io.HDF5FileHandler(str(tmp_path / 'out.h5'), 'run-a')
+    handler.dump(result)
+    tree = set(_fake_h5py.File(handler.location_path, 'r').paths())
+    # the layout of SURVEY 8(f) N2
+    for path in ('/run-a/dmc/state/confs', '/run-a/dmc/state/branching_spec',
+                 '/run-a/dmc/state/props/energy',
+                 '/run-a/dmc/state/props/weight',
+                 '/run-a/dmc/state/props/mask', '/run-a/dmc/proc_spec',
+                 '/run-a/dmc/data/blocks/energy/totals',
+                 '/run-a/dmc/data/blocks/energy/weight_totals',
+                 '/run-a/dmc/data/blocks/weight/totals',
+                 '/run-a/dmc/data/blocks/num_walkers/totals',
+                 '/run-a/dmc/data/blocks/density/totals',
+                 '/run-a/dmc/data/blocks/ss_factor/fdk_sqr_abs/totals',
+                 '/run-a/dmc/data/blocks/ss_factor/fdk_real/totals',
+                 '/run-a/dmc/data/blocks/ss_factor/fdk_imag/totals'):
+        assert path in tree, (path, sorted(tree))
+    back = handler.load()
+    st, st0 = back.state, result.state
+    assert np.array_equal(st.confs, st0.confs)
+    assert np.array_equal(st.props.energy, st0.props.energy)
+    assert np.array_equal(st.props.mask, st0.props.mask)
+    assert np.array_equal(np.asarray(st.branching_spec),
+                          np.asarray(st0.branching_spec))
+    for k in ('energy', 'weight', 'num_walkers', 'ref_energy',
+              'accum_energy', 'max_num_walkers'):
+        assert getattr(st, k) == getattr(st0, k), k
+    assert np.array_equal(back.data.blocks.energy.totals,
+                          result.data.blocks.energy.totals)
+    assert np.array_equal(back.data.blocks.density.totals,
+                          result.data.blocks.density.totals)
+    # and the State read back from the file restarts the B200 procedure
+    again = proc.exec(dmc_exec.ProcInput.from_result(back, proc))
+    assert again.data.blocks.energy.totals.shape == (3,)
+
+
 def test_reference_vmc_proc_drives_b200_sampling(ref, doubled):
     import attr
     from phd_qmclib.mrbp_qmc import Spec, vmc_exec
