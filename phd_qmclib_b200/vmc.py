@@ -102,22 +102,55 @@ class CoreFuncs:
 core_funcs = CoreFuncs()
 
 
+def chains_before(dist, num_chains: int) -> int:
+    """Number of chains on the ranks below this one (plumbing through an
+    initialised ``torch.distributed`` process group)."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    t_ = torch.zeros(world, dtype=torch.int64)
+    t_[rank] = int(num_chains)
+    if str(dist.get_backend()) == 'nccl':
+        t_ = t_.cuda()
+    dist.all_reduce(t_)
+    return int(t_[:rank].sum().item())
+
+
 @dataclass(frozen=True)
 class Sampling:
-    """The spec of a VMC sampling (reference mrbp_qmc/vmc.py:69-170)."""
+    """The spec of a VMC sampling (reference mrbp_qmc/vmc.py:69-170).
+
+    Engine-only options: ``device``; ``chain_offset`` (global index of the
+    first chain of this sampling: chains are keyed by it in the counter-based
+    RNG); ``dist`` (an initialised ``torch.distributed``-like module: every
+    rank runs its own batch of chains -- they never interact, so there is no
+    data-path collective -- and ``chain_offset`` becomes the number of chains
+    on the lower ranks, which needs ``rng_seed`` to be given and equal on all
+    ranks)."""
     model_spec: t.Any
     move_spread: float
     rng_seed: t.Optional[int] = None
     ssf_est_spec: t.Optional[SSFEstSpec] = None
     device: int = 0
     chain_offset: int = 0
+    dist: t.Any = None
     _cache: dict = field(default_factory=dict, init=False, repr=False,
                          compare=False)
 
     def __post_init__(self):
         if self.rng_seed is None:
+            if self.dist is not None and self.dist.get_world_size() > 1:
+                raise ValueError('rng_seed must be given (and equal on every '
+                                 'rank) when the chains are spread over '
+                                 'ranks')
             seed = int(np.random.SeedSequence().generate_state(1)[0])
             object.__setattr__(self, 'rng_seed', seed)
+
+    def _chain_offset(self, num_chains: int) -> int:
+        """Global index of this rank's first chain: the chains of the lower
+        ranks come first."""
+        if self.dist is None or self.dist.get_world_size() == 1:
+            return int(self.chain_offset)
+        return int(self.chain_offset) + chains_before(self.dist, num_chains)
 
     @property
     def tpf_params(self) -> TPFParams:
@@ -189,7 +222,8 @@ class Sampling:
                              z_max,
                              ssf_num_modes=0 if sp.assume_none
                              else sp.num_modes,
-                             chain_offset=self.chain_offset,
+                             chain_offset=self._chain_offset(
+                                 1 if single else len(conf)),
                              proposal=self._proposal)
         return single
 

@@ -202,3 +202,33 @@ def test_sampling_sharded_needs_a_seed():
     assert smp.local_capacity == 25 and smp.state_props_shape == (25,)
     assert [dmc.slab_bounds(10, 4, r) for r in range(4)] == [
         (0, 3), (3, 6), (6, 8), (8, 10)]
+
+
+def _vmc_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from phd_qmclib_b200 import model, vmc
+        spec = model.Spec(0, 1, 4, 16, 16, 4)
+        smp = vmc.Sampling(spec, 0.25, rng_seed=5, dist=dist, chain_offset=7)
+        q.put((rank, smp._chain_offset(10 + rank)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_vmc_chains_are_numbered_across_ranks():
+    """Rank r's chains follow those of the lower ranks in the RNG keying
+    (10, 11 and 12 chains on ranks 0, 1, 2; base offset 7)."""
+    world, port = 3, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_vmc_worker, args=(r, world, port, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == {0: 7, 1: 17, 2: 28}
