@@ -383,3 +383,63 @@ def test_vmc_gaussian_proposal_sampler(oracle):
     assert scaled_err(blk.iter_props.energy, a['energy'][0]) < 1e-11
     with pytest.raises(TypeError):
         vmc_ndf.Sampling(model_spec=spec)
+
+
+def test_dmc_long_run_is_stable_and_reproducible():
+    """51 200 time steps (400 blocks of 128, replayed CUDA graph): the
+    population stays under control, nothing overflows the capacity or turns
+    NaN, the energy agrees with the frozen reference run far inside its error
+    bar budget, and a second engine with the same seed reproduces the first
+    blocks bit for bit."""
+    from phd_qmclib_b200 import dmc
+    g = golden('dmc_stat_ll_n16.npz')
+    p = g['params']
+    nop = int(p[3])
+
+    class _Spec:
+        params, obf_params, tbf_params = p[:12], p[12:19], p[19:]
+        boson_number, supercell_size = nop, float(p[4])
+        boundaries = (0.0, float(p[4]))
+        sys_conf_shape = (2, nop)
+
+    def sampling():
+        return dmc.Sampling(_Spec, float(g['time_step']),
+                            int(g['max_num_walkers']), int(g['n_target']),
+                            num_walkers_control_factor=float(g['nwc_factor']),
+                            rng_seed=4242, reblock_max_order=7)
+
+    a = sampling()
+    it = a.blocks(a.build_state(g['ini_confs']), 128, 0)
+    e_sum, w_sum, first = [], [], []
+    for b in range(400):
+        blk = next(it)
+        ip = blk.iter_props
+        assert np.all(np.isfinite(ip.energy)) and np.all(ip.weight > 0)
+        nw = ip.num_walkers.astype(np.int64)
+        assert nw.min() > 0.7 * int(g['n_target'])
+        assert nw.max() < int(g['max_num_walkers'])
+        if b < 5:
+            first.append((ip.energy.copy(), nw.copy()))
+        if b >= 20:
+            e_sum.append(ip.energy.sum())
+            w_sum.append(ip.weight.sum())
+    assert a.engine.dmc_scalars().capacity_hits == 0
+    assert int(a.engine.dmc_scalars().step) == 400 * 128
+    e, err = ratio_mean_error(e_sum, w_sum)
+    e_ref, err_ref = float(g['ref_energy_mean']), float(g['ref_energy_err'])
+    err_ref = max(err_ref, ratio_mean_error(g['block_energy'],
+                                            g['block_weight'])[1])
+    assert abs(e - e_ref) < 4 * np.hypot(err, err_ref), (e / nop, e_ref / nop)
+    # the on-device reblocking saw every step of every block
+    otf = a.otf_reblock_data()
+    assert otf['energy']['NUM_BLOCKS'].tolist() == [
+        400 * 128 >> k for k in range(8)]
+    mean_e = otf['energy']['MEANS'][0] / otf['energy']['NUM_BLOCKS'][0]
+    mean_w = otf['weight']['MEANS'][0] / otf['weight']['NUM_BLOCKS'][0]
+    assert abs(mean_e / mean_w / nop - e / nop) < 5e-3
+    b_ = sampling()
+    it2 = b_.blocks(b_.build_state(g['ini_confs']), 128, 0)
+    for en, nw in first:
+        ip = next(it2).iter_props
+        assert np.array_equal(ip.energy, en)
+        assert np.array_equal(ip.num_walkers.astype(np.int64), nw)
