@@ -387,7 +387,7 @@ __device__ __forceinline__ void pair_tile(
         //   den_f = sin(a_i - a_j) / gamma_f,
         //   num_f = (mu_f / gamma_f) cos(a_i - a_j),  mu_f < 0,
         // and the column-table variant each pair needs: bit 1 = unwrapped
-        // (cos > 0 <=> num_f < 0), bit 0 = sigma > 0
+        // (cos > 0 <=> num_f < 0), bit 0 = sign bit of den_f
         double den_f[TB], num_f[TB];
         double2 V[TB];
 #pragma unroll
@@ -399,7 +399,7 @@ __device__ __forceinline__ void pair_tile(
         for (int c1 = 0; c1 < TB; ++c1) {
             unsigned hn = (unsigned) __double2hiint(num_f[c1]);
             unsigned hd = (unsigned) __double2hiint(den_f[c1]);
-            unsigned v = ((hn >> 31) << 1) + ((hn ^ hd) >> 31);
+            unsigned v = ((hn >> 31) << 1) + (hd >> 31);
             V[c1] = *reinterpret_cast<const double2 *>(pv + v * vstride);
         }
         // next column particle's far tables, in flight during phase 2
@@ -491,10 +491,14 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
                                               rca[c] * M.inv_gam);
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
-                    // v = 2 * unwrapped + (sigma > 0); u_j' = u_j + sigma psi
+                    // v = 2 * unwrapped + [sin(a_i - a_j) < 0]: the two sign
+                    // bits as they come; sigma > 0 <=> the bits differ
+                    // (unwrapped: sin > 0; wrapped: sin < 0);
+                    // u_j' = u_j + sigma psi
                     const int w = (v & 2) ? 0 : 1;
                     const double cp = M.cpsi[w];
-                    const double sp = (v & 1) ? M.spsi[w] : -M.spsi[w];
+                    const double sp = (((v >> 1) ^ v) & 1) ? M.spsi[w]
+                                                           : -M.spsi[w];
                     sm.var(g, v, c)[I] = make_double2(
                         fma(rsu[c], cp, rcu[c] * sp),
                         fma(rcu[c], cp, -(rsu[c] * sp)));
