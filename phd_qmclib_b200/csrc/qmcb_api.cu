@@ -148,6 +148,9 @@ struct qmcb_handle {
     double *vmc_sum_e = nullptr, *vmc_sum_ssf = nullptr, *vmc_acc = nullptr;
 
     // multi-GPU
+    cudaStream_t pc_stream = nullptr;   // all-reduce + population control of
+    cudaEvent_t ev_branched = nullptr;  // a step run here, next to the step
+    cudaEvent_t ev_controlled = nullptr;    // kernel (which needs neither)
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
     long long *d_counts = nullptr;      // [world] live walkers per rank
@@ -790,6 +793,12 @@ void qmcb_destroy(qmcb_handle *h)
     cudaFree(h->d_counts);
     cudaFree(h->rb.sum); cudaFree(h->rb.sqr); cudaFree(h->rb.nblk);
     cudaFree(h->cs_confs); cudaFree(h->cs_ln0); cudaFree(h->cs_work);
+    if (h->pc_stream) {
+        cudaStreamSynchronize(h->pc_stream);
+        cudaStreamDestroy(h->pc_stream);
+    }
+    if (h->ev_branched) cudaEventDestroy(h->ev_branched);
+    if (h->ev_controlled) cudaEventDestroy(h->ev_controlled);
     if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
     for (auto ev : h->step_ev) cudaEventDestroy(ev);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1266,13 +1275,20 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
             B, h->C, L, h->comm ? 0 : 1);
         if (h->comm) {
             // population control needs the GLOBAL {sum E, W}
-            // (qmc_base/dmc.py:758-771); 16 bytes, in place
+            // (qmc_base/dmc.py:758-771): 16 bytes, all-reduced in place, then
+            // dmc_finalize.  The step kernel of this time step needs neither
+            // (it reads E_ref of the previous step and its own step index
+            // from ctl->tcur), so both run on a second stream next to it; the
+            // next step's branching waits for them.
+            CUDA_TRY(h, cudaEventRecord(h->ev_branched, h->stream));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->pc_stream, h->ev_branched, 0));
             NCCL_TRY(h, nccl_api()->AllReduce(
                             (const void *) ((char *) B.ctl
                                             + offsetof(DmcCtl, red)),
                             (void *) ((char *) B.ctl + offsetof(DmcCtl, red)),
-                            2, ncclDouble, ncclSum, h->comm, h->stream));
-            dmc_finalize_kernel<<<1, 32, 0, h->stream>>>(B, h->C, L);
+                            2, ncclDouble, ncclSum, h->comm, h->pc_stream));
+            dmc_finalize_kernel<<<1, 32, 0, h->pc_stream>>>(B, h->C, L);
+            CUDA_TRY(h, cudaEventRecord(h->ev_controlled, h->pc_stream));
         }
         if (h->profile_steps)
             CUDA_TRY(h, cudaEventRecord(h->step_ev[2 * i], h->stream));
@@ -1280,6 +1296,8 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
             h->M, g, B, h->C);
         if (h->profile_steps)
             CUDA_TRY(h, cudaEventRecord(h->step_ev[2 * i + 1], h->stream));
+        if (h->comm)
+            CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_controlled, 0));
         return QMCB_OK;
     };
     if (use_graph && (!h->block_graph || h->block_graph_nts != nts)) {
@@ -1669,6 +1687,12 @@ int qmcb_comm_init(qmcb_handle *h, const uint8_t *id, int32_t world_size,
                                h->comm, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaFree(d_tmp));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->pc_stream,
+                                          cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_branched,
+                                         cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_controlled,
+                                         cudaEventDisableTiming));
     return QMCB_OK;
 }
 

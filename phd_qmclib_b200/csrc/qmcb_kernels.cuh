@@ -144,6 +144,9 @@ struct DmcCtl {
     unsigned int done_count;    // CTAs of branch_count_kernel that finished
     unsigned int done_fill;     // CTAs of branch_fill_kernel that finished
     long long block_step0;      // `step` at the start of the block in flight
+    long long tcur;             // time step the step kernel in flight works
+                                // on (set by branch_fill_kernel, so that the
+                                // population control may run next to it)
 };
 
 struct DmcBufs {
@@ -288,8 +291,10 @@ branch_count_kernel(DmcBufs B, DmcConsts C)
 
 // K7: population control (qmc_base/dmc.py:758-771) from the (global) sums in
 // ctl->red, the per-step log, and the hand-over to the next step.  Runs
-// BEFORE the step kernel of the same time step, which therefore reads the
-// step index as ctl->step - 1.
+// before or NEXT TO the step kernel of the same time step (inline at the end
+// of branch_fill_kernel on one rank, on a second stream after the all-reduce
+// on several), which therefore takes its step index from ctl->tcur and only
+// reads what this function does not write: W, and E_ref of parity t & 1.
 __device__ __forceinline__ void dmc_finalize(const DmcBufs &B,
                                              const DmcConsts &C,
                                              const DmcLog &L)
@@ -377,6 +382,7 @@ branch_fill_kernel(DmcBufs B, DmcConsts C, DmcLog L, int finalize)
     if (threadIdx.x == 0) {
         B.ctl->red[0] = red[0];
         B.ctl->red[1] = (double) B.ctl->W;
+        B.ctl->tcur = B.ctl->step;
         if (finalize) dmc_finalize(B, C, L);
     }
 }
@@ -479,7 +485,8 @@ dmc_step_kernel(const __grid_constant__ DevModel M, GroupGeom geom, DmcBufs B,
     const int W = ctl->W;
     const long long s0 = (long long) blockIdx.x * geom.G;
     if (s0 >= W) return;
-    const long long t = ctl->step - 1;      // population control ran first
+    const long long t = ctl->tcur;      // not ctl->step: the population control
+                                        // of this step may still be in flight
     const int par = (int) (t & 1);
     const double eref = ctl->eref[par];
     const double *pconfs = B.confs[par];
