@@ -458,6 +458,9 @@ int alloc_dmc(qmcb_handle *h, const qmcb_dmc_params *p,
                                    CS_BLOCKS * std::max(M3, NB)
                                        * sizeof(double)));
     }
+    // the bin lists of the pure density estimator are sized by the
+    // forward-walking window
+    if (h->dp.density_pfw_nts != p->density_pfw_nts) h->est_log_cap = 0;
     h->dmc_ready = false;
     h->dp = *p;
     for (int i = 0; i < 2; ++i) {
