@@ -634,9 +634,12 @@ int launch_density_step(qmcb_handle *h, long long step_idx)
                 h->den_lists + step_idx * stride, h->den_wrec + step_idx,
                 total, use_smem);
         }
-        density_corr_kernel<<<dim3((unsigned) nrec, 16), 256, 0, h->stream>>>(
-            h->den_lists, h->den_wrec, W_dev, N, stride, corr);
-        const double div = (double) std::min(step_idx + 1, pfw);
+        if (nrec > 0)
+            density_corr_kernel<<<dim3((unsigned) nrec, 16), 256, 0,
+                                  h->stream>>>(h->den_lists, h->den_wrec,
+                                               W_dev, N, stride, corr);
+        const double div = (double) std::max<long long>(
+            1, std::min(step_idx + 1, pfw));
         density_out_kernel<<<(NB + 127) / 128, 128, 0, h->stream>>>(
             total, corr, NB, 1.0 / div, h->den_iter + step_idx * NB);
         CUDA_TRY(h, cudaGetLastError());
