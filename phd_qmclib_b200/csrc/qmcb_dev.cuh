@@ -448,6 +448,45 @@ __device__ __forceinline__ void pair_tile(
     }
 }
 
+// The diagonal tile of a full block: the six pairs c1 < c2 among the thread's
+// own four particles, unrolled, without masks; both ends of a pair are rows of
+// this thread, so the "column" contribution goes straight into T (no
+// shared-memory slot, nothing to fold).  The generic masked tile spends 16
+// pair slots on these 6 pairs.
+__device__ __forceinline__ void pair_diag(
+    const DevModel &M, const GroupSmem &sm, int g, int I,
+    const double (&rsa)[TB], const double (&rca)[TB],
+    const double (&rsu)[TB], const double (&rcu)[TB], PairAcc &acc)
+{
+    const unsigned vstride = 4u * (unsigned) sm.nbp * (unsigned) sizeof(double2);
+    const double s_m = M.s_m_scaled, mu = M.mu;
+#pragma unroll
+    for (int c2 = 1; c2 < TB; ++c2) {
+        const double2 A1 = sm.a1(g, c2)[I];
+        const char *pv = reinterpret_cast<const char *>(sm.var(g, 0, c2) + I);
+#pragma unroll
+        for (int c1 = 0; c1 < c2; ++c1) {
+            const double den_f = fma(rsa[c1], A1.y, -(rca[c1] * A1.x));
+            const double num_f = mu * fma(rca[c1], A1.y, rsa[c1] * A1.x);
+            const unsigned hn = (unsigned) __double2hiint(num_f);
+            const unsigned hd = (unsigned) __double2hiint(den_f);
+            const unsigned v = ((hn >> 31) << 1) + (hd >> 31);
+            const double2 V =
+                *reinterpret_cast<const double2 *>(pv + v * vstride);
+            const bool near = fabs(den_f) < s_m;
+            const double num_n = fma(rsu[c1], V.y, -(rcu[c1] * V.x));
+            const double den_n = fma(rcu[c1], V.y, rsu[c1] * V.x);
+            const double num = near ? num_n : num_f;
+            const double den = near ? den_n : den_f;
+            const double inv = fast_rcp(den);
+            const double t = num * inv;
+            acc.T[c1] += t;
+            acc.T[c2] -= t;
+            acc.K = fma(inv, inv, acc.K);
+        }
+    }
+}
+
 // Evaluate drift, local energy (EF) and/or ln|Psi| (LN) of G walkers held by
 // this CTA.  Thread (g, I) owns particles 4I..4I+3 of walker g, positions in
 // z[] (entries >= nvalid are padding).  Every thread of the CTA must call
@@ -512,6 +551,9 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
     double Tq[TB] = {0., 0., 0., 0.};   // column sums received from others
     const bool pairs = active && !M.is_ideal;
     const bool even = (nb & 1) == 0;
+    // drift / energy kernels: the diagonal tile of a full block adds both
+    // ends of its pairs to the thread's own rows
+    const bool diag_direct = !LN && EF && nvalid == TB;
     for (int k0 = 0; k0 <= kmax; k0 += kc) {
         const int k1 = min(k0 + kc, kmax + 1);
         if (pairs) {
@@ -521,7 +563,9 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
                 int J = I + k;
                 if (J >= nb) J -= nb;
                 const int nvj = min(TB, M.nop - TB * J);
-                if (LN || k == 0 || nvalid < TB || nvj < TB)
+                if (k == 0 && diag_direct)
+                    pair_diag(M, sm, g, I, rsa, rca, rsu, rcu, acc);
+                else if (LN || k == 0 || nvalid < TB || nvj < TB)
                     pair_tile<LN, EF, true>(M, sm, g, J, k - k0, k == 0,
                                             nvalid, nvj, rsa, rca, rsu, rcu,
                                             acc);
@@ -537,6 +581,7 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
                 for (int k = k0; k < k1; ++k) {
                     // slot k, column I was written by row block I - k
                     if (k > 0 && even && k == kmax && I < kmax) continue;
+                    if (k == 0 && diag_direct) continue;
 #pragma unroll
                     for (int c = 0; c < TB; ++c)
                         Tq[c] += sm.q(g, k - k0, c)[I];
