@@ -381,8 +381,12 @@ __device__ __forceinline__ void pair_tile(
     const double s_m = M.s_m_scaled;
     double2 A1 = *reinterpret_cast<const double2 *>(pa1);
     const double mu = M.mu;
+    // a masked tile whose column block is the ragged last one stops at its
+    // last particle (drift / energy kernels; measured slower in the VMC
+    // block kernel, which keeps the fixed trip count)
+    const int ncol = (MASK && !LN) ? nvj : TB;
 #pragma unroll 1
-    for (int c2 = 0; c2 < TB; ++c2) {
+    for (int c2 = 0; c2 < ncol; ++c2) {
         // phase 1: far branch in near units for the four rows,
         //   den_f = sin(a_i - a_j) / gamma_f,
         //   num_f = (mu_f / gamma_f) cos(a_i - a_j),  mu_f < 0,
@@ -403,7 +407,7 @@ __device__ __forceinline__ void pair_tile(
             V[c1] = *reinterpret_cast<const double2 *>(pv + v * vstride);
         }
         // next column particle's far tables, in flight during phase 2
-        if (c2 + 1 < TB) {
+        if (c2 + 1 < ncol) {
             pa1 += cstride;
             A1 = *reinterpret_cast<const double2 *>(pa1);
         }
@@ -446,6 +450,8 @@ __device__ __forceinline__ void pair_tile(
         if (EF) { *pq = fc; pq += nbp; }
         if (LN) { renorm(acc.pf, acc.ef); renorm(acc.pn, acc.en); }
     }
+    if (MASK && EF && !LN)
+        for (int c2 = ncol; c2 < TB; ++c2) { *pq = 0.0; pq += nbp; }
 }
 
 // The diagonal tile of a full block: the six pairs c1 < c2 among the thread's
