@@ -381,12 +381,8 @@ __device__ __forceinline__ void pair_tile(
     const double s_m = M.s_m_scaled;
     double2 A1 = *reinterpret_cast<const double2 *>(pa1);
     const double mu = M.mu;
-    // a masked tile whose column block is the ragged last one stops at its
-    // last particle (drift / energy kernels; measured slower in the VMC
-    // block kernel, which keeps the fixed trip count)
-    const int ncol = (MASK && !LN) ? nvj : TB;
 #pragma unroll 1
-    for (int c2 = 0; c2 < ncol; ++c2) {
+    for (int c2 = 0; c2 < TB; ++c2) {
         // phase 1: far branch in near units for the four rows,
         //   den_f = sin(a_i - a_j) / gamma_f,
         //   num_f = (mu_f / gamma_f) cos(a_i - a_j),  mu_f < 0,
@@ -407,7 +403,7 @@ __device__ __forceinline__ void pair_tile(
             V[c1] = *reinterpret_cast<const double2 *>(pv + v * vstride);
         }
         // next column particle's far tables, in flight during phase 2
-        if (c2 + 1 < ncol) {
+        if (c2 + 1 < TB) {
             pa1 += cstride;
             A1 = *reinterpret_cast<const double2 *>(pa1);
         }
@@ -450,8 +446,6 @@ __device__ __forceinline__ void pair_tile(
         if (EF) { *pq = fc; pq += nbp; }
         if (LN) { renorm(acc.pf, acc.ef); renorm(acc.pn, acc.en); }
     }
-    if (MASK && EF && !LN)
-        for (int c2 = ncol; c2 < TB; ++c2) { *pq = 0.0; pq += nbp; }
 }
 
 // The diagonal tile of a full block: the six pairs c1 < c2 among the thread's
@@ -490,6 +484,57 @@ __device__ __forceinline__ void pair_diag(
             acc.T[c2] -= t;
             acc.K = fma(inv, inv, acc.K);
         }
+    }
+}
+
+// A ragged tile of the drift / energy kernels: the row block and/or the
+// column block is the last, partly filled one (N not a multiple of 4), or the
+// tile is the diagonal of such a block.  Only the valid pairs are evaluated
+// (the bounds are the same for all lanes of a warp in the interleaved
+// mapping), so the thread that owns the ragged block does not become the
+// straggler every barrier waits for.
+__device__ __forceinline__ void pair_ragged(
+    const DevModel &M, const GroupSmem &sm, int g, int J, int qslot,
+    bool diag, int nvalid, int nvj, const double (&rsa)[TB],
+    const double (&rca)[TB], const double (&rsu)[TB],
+    const double (&rcu)[TB], PairAcc &acc)
+{
+    const int nbp = sm.nbp;
+    const unsigned vstride = 4u * (unsigned) nbp * (unsigned) sizeof(double2);
+    const double s_m = M.s_m_scaled, mu = M.mu;
+    double *pq = sm.q(g, qslot, 0) + J;
+    for (int c2 = 0; c2 < TB; ++c2) {
+        double fc = 0.0;
+        if (c2 < nvj) {
+            const double2 A1 = sm.a1(g, c2)[J];
+            const char *pv =
+                reinterpret_cast<const char *>(sm.var(g, 0, c2) + J);
+#pragma unroll
+            for (int c1 = 0; c1 < TB; ++c1) {
+                if (c1 < nvalid && (!diag || c1 < c2)) {
+                    const double den_f = fma(rsa[c1], A1.y, -(rca[c1] * A1.x));
+                    const double num_f =
+                        mu * fma(rca[c1], A1.y, rsa[c1] * A1.x);
+                    const unsigned hn = (unsigned) __double2hiint(num_f);
+                    const unsigned hd = (unsigned) __double2hiint(den_f);
+                    const unsigned v = ((hn >> 31) << 1) + (hd >> 31);
+                    const double2 V =
+                        *reinterpret_cast<const double2 *>(pv + v * vstride);
+                    const bool near = fabs(den_f) < s_m;
+                    const double num_n = fma(rsu[c1], V.y, -(rcu[c1] * V.x));
+                    const double den_n = fma(rcu[c1], V.y, rsu[c1] * V.x);
+                    const double num = near ? num_n : num_f;
+                    const double den = near ? den_n : den_f;
+                    const double inv = fast_rcp(den);
+                    const double t = num * inv;
+                    acc.T[c1] += t;
+                    fc -= t;
+                    acc.K = fma(inv, inv, acc.K);
+                }
+            }
+        }
+        *pq = fc;
+        pq += nbp;
     }
 }
 
@@ -571,6 +616,9 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
                 const int nvj = min(TB, M.nop - TB * J);
                 if (k == 0 && diag_direct)
                     pair_diag(M, sm, g, I, rsa, rca, rsu, rcu, acc);
+                else if (!LN && (k == 0 || nvalid < TB || nvj < TB))
+                    pair_ragged(M, sm, g, J, k - k0, k == 0, nvalid, nvj,
+                                rsa, rca, rsu, rcu, acc);
                 else if (LN || k == 0 || nvalid < TB || nvj < TB)
                     pair_tile<LN, EF, true>(M, sm, g, J, k - k0, k == 0,
                                             nvalid, nvj, rsa, rca, rsu, rcu,
