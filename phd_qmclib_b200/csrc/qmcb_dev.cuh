@@ -453,8 +453,9 @@ __device__ __forceinline__ void pair_tile(
 // this thread, so the "column" contribution goes straight into T (no
 // shared-memory slot, nothing to fold).  The generic masked tile spends 16
 // pair slots on these 6 pairs.
+template <bool RAGGED>
 __device__ __forceinline__ void pair_diag(
-    const DevModel &M, const GroupSmem &sm, int g, int I,
+    const DevModel &M, const GroupSmem &sm, int g, int I, int nvalid,
     const double (&rsa)[TB], const double (&rca)[TB],
     const double (&rsu)[TB], const double (&rcu)[TB], PairAcc &acc)
 {
@@ -462,6 +463,7 @@ __device__ __forceinline__ void pair_diag(
     const double s_m = M.s_m_scaled, mu = M.mu;
 #pragma unroll
     for (int c2 = 1; c2 < TB; ++c2) {
+        if (RAGGED && c2 >= nvalid) break;      // last, partly filled block
         const double2 A1 = sm.a1(g, c2)[I];
         const char *pv = reinterpret_cast<const char *>(sm.var(g, 0, c2) + I);
 #pragma unroll
@@ -602,10 +604,17 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
     double Tq[TB] = {0., 0., 0., 0.};   // column sums received from others
     const bool pairs = active && !M.is_ideal;
     const bool even = (nb & 1) == 0;
-    // drift / energy kernels: the diagonal tile of a full block adds both
-    // ends of its pairs to the thread's own rows
-    const bool diag_direct = !LN && EF && nvalid == TB;
-    for (int k0 = 0; k0 <= kmax; k0 += kc) {
+    // drift / energy kernels: the diagonal tile adds both ends of its pairs
+    // to the thread's own rows and needs no column-sum slot, so the slots
+    // (and the barrier pairs around their fold) serve k = 1 .. kmax only
+    constexpr bool diag_direct = !LN && EF;
+    if (diag_direct && pairs) {
+        if (nvalid == TB)
+            pair_diag<false>(M, sm, g, I, nvalid, rsa, rca, rsu, rcu, acc);
+        else
+            pair_diag<true>(M, sm, g, I, nvalid, rsa, rca, rsu, rcu, acc);
+    }
+    for (int k0 = diag_direct ? 1 : 0; k0 <= kmax; k0 += kc) {
         const int k1 = min(k0 + kc, kmax + 1);
         if (pairs) {
             for (int k = k0; k < k1; ++k) {
@@ -614,9 +623,7 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
                 int J = I + k;
                 if (J >= nb) J -= nb;
                 const int nvj = min(TB, M.nop - TB * J);
-                if (k == 0 && diag_direct)
-                    pair_diag(M, sm, g, I, rsa, rca, rsu, rcu, acc);
-                else if (!LN && (k == 0 || nvalid < TB || nvj < TB))
+                if (!LN && (k == 0 || nvalid < TB || nvj < TB))
                     pair_ragged(M, sm, g, J, k - k0, k == 0, nvalid, nvj,
                                 rsa, rca, rsu, rcu, acc);
                 else if (LN || k == 0 || nvalid < TB || nvj < TB)
@@ -635,7 +642,6 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
                 for (int k = k0; k < k1; ++k) {
                     // slot k, column I was written by row block I - k
                     if (k > 0 && even && k == kmax && I < kmax) continue;
-                    if (k == 0 && diag_direct) continue;
 #pragma unroll
                     for (int c = 0; c < TB; ++c)
                         Tq[c] += sm.q(g, k - k0, c)[I];
