@@ -349,8 +349,8 @@ __host__ __device__ inline int group_smem_doubles(int G, int nbp, int nb,
 // Result of a walker-group evaluation, per thread.
 struct EvalOut {
     double F[TB];       // drift of the thread's own particles
-    double energy;      // local energy of the walker (valid on every thread)
-    double lnpsi;       // ln|Psi| of the walker (valid on every thread)
+    double energy;      // local energy of the walker (on every thread of the
+    double lnpsi;       // walker if BCAST, else on its thread I == 0) / ln|Psi|
 };
 
 // Accumulators of one thread over its pair tiles.
@@ -545,7 +545,10 @@ __device__ __forceinline__ void pair_ragged(
 // z[] (entries >= nvalid are padding).  Every thread of the CTA must call
 // this (it synchronises); `active` is false for surplus threads and for
 // walkers that are not live.
-template <bool LN, bool EF>
+// BCAST: E_L and ln|Psi| of the walker are needed on every one of its threads
+// (the Metropolis test of the VMC kernel); otherwise only thread I == 0 adds
+// up the per-thread partials.
+template <bool LN, bool EF, bool BCAST = true>
 __device__ __forceinline__ void group_eval(const DevModel &M,
                                            const GroupSmem &sm, int g, int I,
                                            bool active, const double (&z)[TB],
@@ -614,26 +617,36 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
         else
             pair_diag<true>(M, sm, g, I, nvalid, rsa, rca, rsu, rcu, acc);
     }
+    // per-thread constants of the tile loop: the last tile this thread
+    // computes / folds (antipodal block column of an even ring: the first
+    // half of the row blocks computes it, the second half receives it) and
+    // the ragged last block (N not a multiple of 4)
+    const int k_last_row = (even && I >= kmax) ? kmax - 1 : kmax;
+    const int k_skip_col = (even && I < kmax) ? kmax : -1;
+    const int j_ragged = (M.nop % TB) ? nb - 1 : -1;
+    const bool row_ragged = nvalid < TB;
     for (int k0 = diag_direct ? 1 : 0; k0 <= kmax; k0 += kc) {
         const int k1 = min(k0 + kc, kmax + 1);
         if (pairs) {
-            for (int k = k0; k < k1; ++k) {
-                // antipodal block column of an even ring: half the rows
-                if (k > 0 && even && k == kmax && I >= kmax) break;
+            const int ke = min(k1, k_last_row + 1);
+            for (int k = k0; k < ke; ++k) {
                 int J = I + k;
                 if (J >= nb) J -= nb;
-                const int nvj = min(TB, M.nop - TB * J);
-                if (!LN && (k == 0 || nvalid < TB || nvj < TB))
+                const bool ragged = row_ragged || J == j_ragged;
+                if (!LN && (k == 0 || ragged)) {
+                    const int nvj = min(TB, M.nop - TB * J);
                     pair_ragged(M, sm, g, J, k - k0, k == 0, nvalid, nvj,
                                 rsa, rca, rsu, rcu, acc);
-                else if (LN || k == 0 || nvalid < TB || nvj < TB)
+                } else if (LN || k == 0 || ragged) {
+                    const int nvj = min(TB, M.nop - TB * J);
                     pair_tile<LN, EF, true>(M, sm, g, J, k - k0, k == 0,
                                             nvalid, nvj, rsa, rca, rsu, rcu,
                                             acc);
-                else
+                } else {
                     pair_tile<LN, EF, false>(M, sm, g, J, k - k0, false,
-                                             nvalid, nvj, rsa, rca, rsu, rcu,
+                                             nvalid, TB, rsa, rca, rsu, rcu,
                                              acc);
+                }
             }
         }
         if (EF) {
@@ -641,7 +654,7 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
             if (pairs) {
                 for (int k = k0; k < k1; ++k) {
                     // slot k, column I was written by row block I - k
-                    if (k > 0 && even && k == kmax && I < kmax) continue;
+                    if (k == k_skip_col) continue;
 #pragma unroll
                     for (int c = 0; c < TB; ++c)
                         Tq[c] += sm.q(g, k - k0, c)[I];
@@ -679,7 +692,7 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
     }
     __syncthreads();
     double esum = 0.0, lsum = 0.0;
-    if (active) {
+    if (active && (BCAST || I == 0)) {
         for (int t = 0; t < nb; ++t) {
             if (EF) esum += sm.red(g, 0)[t];
             if (LN) lsum += sm.red(g, 1)[t];

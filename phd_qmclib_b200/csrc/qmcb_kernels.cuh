@@ -108,7 +108,7 @@ model_eval_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                 store4(a.state_confs + b * 2 * N, x.I, nvalid, vec_ok, z);
         }
         EvalOut o;
-        group_eval<LN, EF>(M, sm, x.g, x.I, active, z, nvalid, o);
+        group_eval<LN, EF, false>(M, sm, x.g, x.I, active, z, nvalid, o);
         if (active) {
             if (EF && a.drift)
                 store4(a.drift + b * N, x.I, nvalid, vec_ok, o.F);
@@ -526,7 +526,7 @@ dmc_step_kernel(const __grid_constant__ DevModel M, GroupGeom geom, DmcBufs B,
         store4(nconfs + s * 2 * N, x.I, nvalid, vec_ok, z);
     }
     EvalOut o;
-    group_eval<false, true>(M, sm, x.g, x.I, active, z, nvalid, o);
+    group_eval<false, true, false>(M, sm, x.g, x.I, active, z, nvalid, o);
     if (active) {
         double *nc = nconfs + s * 2 * N;
         store4(nc + N, x.I, nvalid, vec_ok, o.F);
