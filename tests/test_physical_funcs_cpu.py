@@ -31,6 +31,20 @@ class OracleEngine:
     def fourier_density_k(self, confs, kz_set):
         return self.o.fourier_density_k(self.p, confs, kz_set)
 
+    def cs_load(self, sys_conf_set, ini_wf_abs_log_set=None):
+        self.cs = (np.asarray(sys_conf_set), np.asarray(ini_wf_abs_log_set))
+
+    def cs_variance(self, trial_spec=None, want_sets=False):
+        from phd_qmclib_b200.model import param_block
+        p = self.p if trial_spec is None else param_block(trial_spec)
+        o = self.o.model_eval(p, self.cs[0], want=('lnpsi', 'energy'))
+        var, eref = self.o.weighed_variance(o['lnpsi'], self.cs[1],
+                                            o['energy'])
+        out = dict(variance=var, ref_energy=eref)
+        if want_sets:
+            out.update(wf_abs_log=o['lnpsi'], energy=o['energy'])
+        return out
+
 
 @pytest.fixture(scope='module')
 def ref():
@@ -83,3 +97,25 @@ def test_physical_funcs_broadcast_like_the_reference(ref, name, monkeypatch):
     got = pf.fourier_density(kz, confs)
     assert got.shape == want.shape == (3, 4, 4)
     assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
+
+
+def test_cs_optimizer_mirror_on_the_oracle(monkeypatch):
+    """Host logic of CSWFOptimizer (update_spec -> trial parameters ->
+    objective) with the oracle standing in for the engine, against the
+    objective values of the live reference frozen in tests/golden/."""
+    from conftest import golden, golden_names
+    from phd_qmclib_b200 import engine as engine_mod, model
+    monkeypatch.setattr(engine_mod, 'Engine', OracleEngine)
+    for name in golden_names('cswf_'):
+        g = golden(name)
+        kw = dict(zip([str(k) for k in g['spec_keys']], g['spec_vals']))
+        opt = model.CSWFOptimizer(model.Spec(**kw), g['confs'],
+                                  g['ini_lnpsi'])
+        for k, rm in enumerate(g['cutoffs']):
+            scale = max(g['variance'][k],
+                        1e-12 * np.mean(g['energy'][k] ** 2))
+            assert abs(opt.principal_function(rm) - g['variance'][k]) \
+                < 1e-9 * scale
+            # scipy hands the objective a length-1 array
+            assert opt.principal_function(np.array([rm])) \
+                == opt.principal_function(rm)
