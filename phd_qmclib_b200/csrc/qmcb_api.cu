@@ -440,9 +440,9 @@ int alloc_dmc(qmcb_handle *h, const qmcb_dmc_params *p,
             for (int i = 0; i < 2; ++i)
                 CUDA_TRY(h, cudaMalloc(&h->ssf_aux[i],
                                        cap * M3 * sizeof(double)));
-        // pure mode: 16-bit bin lists instead of per-slot histograms
+        // 16-bit bin lists instead of per-slot histograms
         // (QMCB_DENSITY_HIST keeps the histogram path, for A/B tests)
-        h->den_lists_mode = NB && p->density_as_pure && NB <= 65536
+        h->den_lists_mode = NB && NB <= 65536
                             && !getenv("QMCB_DENSITY_HIST");
         if (NB) {
             const int nh = h->den_lists_mode ? 0
@@ -450,7 +450,7 @@ int alloc_dmc(qmcb_handle *h, const qmcb_dmc_params *p,
             for (int i = 0; i < nh; ++i)
                 CUDA_TRY(h, cudaMalloc(&h->den_hist[i],
                                        cap * NB * sizeof(double)));
-            CUDA_TRY(h, cudaMalloc(&h->den_total, 2 * NB * sizeof(double)));
+            CUDA_TRY(h, cudaMalloc(&h->den_total, 3 * NB * sizeof(double)));
             CUDA_TRY(h, cudaMalloc(&h->den_hi, sizeof(int)));
         }
         if (M3 || NB)
@@ -508,8 +508,11 @@ int ensure_est_log(qmcb_handle *h, long long nts)
     if (h->den_lists_mode) {
         cudaFree(h->den_lists); cudaFree(h->den_wrec);
         h->den_lists = nullptr; h->den_wrec = nullptr;
-        const long long steps = std::min<long long>(
-            nts, std::max<long long>(1, h->dp.density_pfw_nts));
+        // pure: the steps of the forward-walking window; mixed: all steps
+        const long long steps = h->dp.density_as_pure
+            ? std::min<long long>(
+                  nts, std::max<long long>(1, h->dp.density_pfw_nts))
+            : nts;
         CUDA_TRY(h, cudaMalloc(&h->den_lists,
                                (size_t) steps * h->B.cap * h->M.nop
                                    * sizeof(unsigned short)));
@@ -614,11 +617,13 @@ int launch_density_step(qmcb_handle *h, long long step_idx)
     const int pbuf = pure ? 0 : (int) (step_idx & 1);
     int *W_dev = (int *) ((char *) B.ctl + offsetof(DmcCtl, W));
     if (h->den_lists_mode) {
-        double *total = h->den_total, *corr = h->den_total + NB;
+        // mixed mode: one running total per step parity, every step recorded
+        double *total = h->den_total + (size_t) pbuf * NB;
+        double *corr = h->den_total + 2 * (size_t) NB;
         const long long stride = (long long) B.cap * N;
-        const long long nrec = std::min<long long>(
-            std::min(step_idx + 1, pfw), h->den_lists_steps);
-        if (step_idx < nrec) {
+        const bool record = pure ? step_idx < std::min(pfw, h->den_lists_steps)
+                                 : step_idx < h->den_lists_steps;
+        if (record) {
             const double *confs =
                 B.confs[(int) ((h->step_host + step_idx) & 1)];
             const size_t sm_bytes = (size_t) NB * sizeof(unsigned int);
@@ -634,12 +639,25 @@ int launch_density_step(qmcb_handle *h, long long step_idx)
                 h->den_lists + step_idx * stride, h->den_wrec + step_idx,
                 total, use_smem);
         }
+        // recorded steps whose counts in the slots beyond W_t must go
+        long long nrec;
+        int first = 0, every = 1;
+        if (pure) {
+            nrec = std::min<long long>(std::min(step_idx + 1, pfw),
+                                       h->den_lists_steps);
+        } else {
+            first = pbuf; every = 2;
+            nrec = std::min(step_idx, h->den_lists_steps - 1) / 2 + 1;
+            if (first > step_idx) nrec = 0;
+        }
         if (nrec > 0)
             density_corr_kernel<<<dim3((unsigned) nrec, 16), 256, 0,
                                   h->stream>>>(h->den_lists, h->den_wrec,
-                                               W_dev, N, stride, corr);
-        const double div = (double) std::max<long long>(
-            1, std::min(step_idx + 1, pfw));
+                                               W_dev, N, stride, first, every,
+                                               corr);
+        const double div = pure ? (double) std::max<long long>(
+                                      1, std::min(step_idx + 1, pfw))
+                                : 1.0;
         density_out_kernel<<<(NB + 127) / 128, 128, 0, h->stream>>>(
             total, corr, NB, 1.0 / div, h->den_iter + step_idx * NB);
         CUDA_TRY(h, cudaGetLastError());
@@ -1250,7 +1268,7 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
                                                 cap_sz * NB * sizeof(double),
                                                 h->stream));
             CUDA_TRY(h, cudaMemsetAsync(h->den_total, 0,
-                                        2 * (size_t) NB * sizeof(double),
+                                        3 * (size_t) NB * sizeof(double),
                                         h->stream));
             CUDA_TRY(h, cudaMemsetAsync(h->den_hi, 0, sizeof(int),
                                         h->stream));

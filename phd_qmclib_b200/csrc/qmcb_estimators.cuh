@@ -341,10 +341,12 @@ density_hist_kernel(const double *confs, const int *ref, const int *W_dev,
 
 
 // ---------------------------------------------------------------------------
-// Pure density estimator without per-slot histograms.  In pure mode the
-// reference ignores the genealogy (quirk Q2): slot s simply accumulates the
-// counts of whatever walker occupies it, and step t sums the rows of the
-// slots that are live at t.  Hence
+// Density estimator without per-slot histograms.  In pure mode the reference
+// ignores the genealogy (quirk Q2): slot s simply accumulates the counts of
+// whatever walker occupies it, and step t sums the rows of the slots that are
+// live at t; in mixed mode it does the same into two buffers by the parity of
+// the step and never resets them within a block (quirk Q3).  Hence, with t'
+// running over the recorded steps (of the same parity in mixed mode),
 //   out(t) = [ sum over recorded steps t' <= t of ALL counts of t' ]
 //            - [ counts of step t' in the slots W_t <= s < W_t' ]   (t' < t)
 // The first term is one running histogram; the second touches only the few
@@ -394,11 +396,14 @@ density_list_kernel(const double *confs, const int *ref, const int *W_dev,
 __global__ void __launch_bounds__(256)
 density_corr_kernel(const unsigned short *lists, const int *W_rec,
                     const int *W_dev, int N, long long step_stride,
-                    double *corr)
+                    int first, int every, double *corr)
 {
-    const long long Wt = *W_dev, Wp = W_rec[blockIdx.x];
+    // recorded steps first, first + every, ...: all of them in pure mode,
+    // those of the current parity in mixed mode
+    const long long tp = first + (long long) every * blockIdx.x;
+    const long long Wt = *W_dev, Wp = W_rec[tp];
     if (Wp <= Wt) return;
-    const unsigned short *l = lists + blockIdx.x * step_stride;
+    const unsigned short *l = lists + tp * step_stride;
     for (long long e = Wt * N + blockIdx.y * blockDim.x + threadIdx.x;
          e < Wp * N; e += (long long) gridDim.y * blockDim.x)
         atomicAdd(corr + l[e], 1.0);
