@@ -314,13 +314,19 @@ def run_b200(args):
     F = flops_per_walker_step(NOP)
     ach_tf = ws_rank * F / (kern_ms * 1e-3) / 1e12
     hbm_gbs = ws_rank * bytes_per_walker_step(NOP) / (kern_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, ncu_view = None, None
     prof_path = os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')
     if os.path.exists(prof_path):
         try:
             tj = json.load(open(prof_path))
             traffic = tj['dram_bytes_per_walker'] * ws_rank / (
                 args.steps * nts)
+            # the executed-instruction view of the same kernel, from the
+            # committed ncu capture (not measured in this run)
+            ncu_view = {k: tj[k] for k in (
+                'fp64_pipe_active_pct', 'issue_active_pct',
+                'warp_instructions_per_launch', 'registers_per_thread',
+                'source') if k in tj}
         except Exception:
             traffic = None
     peaks = {}
@@ -341,6 +347,7 @@ def run_b200(args):
         'step_kernel_share_of_step': kern_ms / max_over_ranks(
             e0.elapsed_time(e1)),
         'traffic': traffic,
+        'ncu': ncu_view,
         'hbm': {'achieved': hbm_gbs, 'peak': peaks.get('hbm_gbs', 6650.0),
                 'unit': 'GB/s',
                 'frac': hbm_gbs / peaks.get('hbm_gbs', 6650.0),
