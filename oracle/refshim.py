@@ -9,8 +9,10 @@ environment (missing third-party modules, removed aliases) and pre-seeds four
 (``np.array(tuple(namedtuple))``, reference ``mrbp_qmc/model.py:582`` and
 ``mrbp_qmc/dmc.py:363,378,393``).
 
-The reference only exists in the builder container: nothing under ``tests/``
-marked ``gpu``, ``bench.py`` or ``__graft_entry__`` may import this module.
+``/root/reference`` only exists in the builder container; on the GPU box the
+tree is the offline install ``baseline/_ref`` (``baseline/install_reference.sh``),
+used by ``bench.py --impl reference`` / the ``cpu_baseline`` leg through
+``oracle/ref_arm.py`` and by the drop-in GPU test, which skips without it.
 """
 import collections
 import collections.abc
@@ -23,7 +25,22 @@ import typing
 
 import numpy as np
 
-REFERENCE_SRC = os.environ.get('QMCB_REFERENCE_SRC', '/root/reference/src')
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference():
+    """$QMCB_REFERENCE_SRC, the builder container's tree, or the offline
+    install under baseline/_ref (baseline/install_reference.sh: unmodified
+    files, git-ignored, travels to the GPU box)."""
+    cands = [os.environ.get('QMCB_REFERENCE_SRC'), '/root/reference/src',
+             os.path.join(_ROOT, 'baseline', '_ref')]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, 'phd_qmclib')):
+            return c
+    return cands[0] or cands[1]
+
+
+REFERENCE_SRC = _find_reference()
 
 _installed = False
 

@@ -443,16 +443,17 @@ class CSWFOptimizer:
 
     @staticmethod
     def weighed_variance(weights_log_set, energy_set, ref_energy=None):
-        """Host restatement kept for API compatibility
-        (``jastrow/model.py:1147-1165``); the optimiser itself reduces on
-        the device."""
-        weights_log_set = np.asarray(weights_log_set)
-        energy_set = np.asarray(energy_set)
-        rel_weights = np.exp(weights_log_set - weights_log_set.max())
-        weight_sum = rel_weights.sum()
-        ref_energy = (rel_weights * energy_set).sum() / weight_sum
-        e_diff = rel_weights * (energy_set - ref_energy) ** 2
-        return e_diff.sum() / weight_sum
+        """Variance of E_L under the weights exp(weights_log_set), about their
+        weighted mean (API of ``jastrow/model.py:1147-1165``; like there,
+        ``ref_energy`` is accepted and not used).  Host-side helper for
+        arrays already on the host -- the optimiser's objective is reduced on
+        the device by ``qmcb_cs_variance`` (``cs_variance_kernel``)."""
+        lw = np.asarray(weights_log_set, dtype=np.float64).ravel()
+        e = np.asarray(energy_set, dtype=np.float64).ravel()
+        w = np.exp(lw - lw.max())       # largest weight is 1: no overflow
+        w /= w.sum()
+        mean = np.dot(w, e)
+        return float(np.dot(w, np.square(e - mean)))
 
     def wf_abs_log_and_energy_set(self, cfc_spec):
         """ln|Psi| and E_L of every configuration under ``cfc_spec``

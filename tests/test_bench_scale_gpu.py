@@ -1,0 +1,208 @@
+"""GPU parity at the populations the bench runs: capacities far beyond one
+branching tile (BR_TILE = 1024 slots), so that the multi-CTA form of
+`sync_branching_spec` (qmc_base/dmc.py:614-655) -- per-CTA counts, the scan of
+the CTA sums by the last CTA to finish, the block-offset carry, the truncation
+at capacity across CTA boundaries and the fixed-order sum of the cloned
+parents' energies (state_energy, qmc_base/dmc.py:759-760) -- is compared with
+the serial oracle on the same Philox streams.  Bit-equal walker counts and
+cloning tables; per-step series to 1e-10."""
+import numpy as np
+import pytest
+
+from conftest import golden, maxnorm_err, rel_err
+
+pytestmark = pytest.mark.gpu
+
+BR_TILE = 1024      # phd_qmclib_b200/csrc/qmcb_kernels.cuh
+
+
+def _spec(p):
+    return (p[:12], p[12:19], p[19:])
+
+
+def _ini(rng, n, nop, size):
+    ini = np.zeros((n, 2, nop))
+    ini[:, 0] = rng.random((n, nop)) * size
+    return ini
+
+
+def _check_state(eng, st):
+    """Cloning table, mask, positions and energies of the yielded state, then
+    the evolved population and the stale-slot energies (quirk Q1)."""
+    s = eng.dmc_get_state()
+    nw = st.num_walkers
+    assert int(s['scalars'].num_walkers) == nw
+    assert np.array_equal(s['cloning_ref'][:nw], st.ref[:nw])
+    assert np.array_equal(s['mask'], st.act['mask'])
+    assert np.allclose(s['confs'][:nw, 0], st.act['confs'][:nw, 0],
+                       rtol=0, atol=1e-9)
+    assert rel_err(s['energy'][:nw], st.act['energy'][:nw]) < 1e-9
+    nx = eng.dmc_get_next()
+    assert np.allclose(nx['confs'][:, 0], st.prev['confs'][:nw, 0], rtol=0,
+                       atol=1e-9)
+    assert maxnorm_err(nx['confs'][:, 1], st.prev['confs'][:nw, 1]) < 1e-8
+    assert rel_err(nx['weight'], st.prev['weight'][:nw]) < 1e-9
+    assert np.allclose(nx['slot_energy'], st.act['energy'], rtol=1e-9,
+                       atol=1e-9)
+
+
+@pytest.mark.parametrize('energy_mode', [0, 1])
+def test_dmc_n100_8192_walkers_vs_oracle(oracle, energy_mode):
+    """BASELINE configs[3] model (N=100) at 8192 target / 10240 slots: ten
+    branching CTAs.  Time step large enough that every step has births and
+    deaths in every CTA."""
+    from phd_qmclib_b200 import engine
+    p = golden('model_lat_n100.npz')['params']
+    nop, size = int(p[3]), float(p[4])
+    target, wmax, nts, dt, seed = 8192, 10240, 6, 2e-3, 1234
+    ini = _ini(np.random.default_rng(100), target, nop, size)
+    st = oracle.DMCState(p, ini, wmax)
+    eng = engine.Engine(_spec(p))
+    dp = eng.dmc_params(dt, wmax, target, 0.5, seed, 0.0, size,
+                        energy_mode=energy_mode)
+    eng.dmc_init(dp, ini)
+    births = deaths = 0
+    for _ in range(2):
+        a = st.run_block(seed, dt, target, 0.5, nts, 0.0, size,
+                         energy_mode=energy_mode)
+        b = eng.dmc_run_block(nts)
+        assert np.array_equal(a['num_walkers'], b['num_walkers'])
+        for k in ('energy', 'weight', 'ref_energy', 'accum_energy'):
+            assert rel_err(b[k], a[k]) < 1e-10, k
+        nw = st.num_walkers
+        cnt = np.bincount(st.ref[:nw], minlength=wmax)
+        births += int((cnt > 1).sum())
+        deaths += int((cnt[:int(st.ref[nw - 1]) + 1] == 0).sum())
+    assert births > 10 and deaths > 10      # the test did branch
+    assert st.num_walkers > 5 * BR_TILE
+    _check_state(eng, st)
+    assert eng.dmc_scalars().capacity_hits == 0
+    eng.close()
+
+
+@pytest.mark.parametrize('n_ini,wmax', [(3000, 3500), (2500, 2 * BR_TILE + 1),
+                                        (5000, 5 * BR_TILE)])
+def test_capacity_hit_inside_a_later_cta(oracle, n_ini, wmax):
+    """Quirk Q8 (qmc_base/dmc.py:636-651): the reference fills slots in
+    parent order and drops everything past the capacity.  A reference energy
+    far too low makes every step overflow; the cut falls among the parents of
+    branching CTA >= 2 (and, for wmax = 2049, one slot into the third tile of
+    children; for wmax = 5120 exactly on a tile boundary)."""
+    from phd_qmclib_b200 import engine
+    p = golden('model_ll_n16.npz')['params']
+    nop, size = int(p[3]), float(p[4])
+    ini = _ini(np.random.default_rng(n_ini), n_ini, nop, size)
+    st = oracle.DMCState(p, ini, wmax, ref_energy=60.0)
+    eng = engine.Engine(_spec(p))
+    dp = eng.dmc_params(5e-3, wmax, n_ini, 0.0, 9, 0.0, size)
+    eng.dmc_init(dp, ini, ref_energy=60.0)
+    a = st.run_block(9, 5e-3, n_ini, 0.0, 5, 0.0, size)
+    b = eng.dmc_run_block(5)
+    assert a['num_walkers'].max() == wmax
+    assert np.array_equal(a['num_walkers'], b['num_walkers'])
+    for k in ('energy', 'weight', 'ref_energy', 'accum_energy'):
+        assert rel_err(b[k], a[k]) < 1e-10, k
+    # the last parent that got a slot sits in a CTA with index >= 2
+    nw = st.num_walkers
+    assert nw == wmax
+    assert st.ref[nw - 1] >= 2 * BR_TILE or wmax == 2 * BR_TILE + 1
+    assert eng.dmc_scalars().capacity_hits >= 1
+    _check_state(eng, st)
+    eng.close()
+
+
+def test_dmc_config3_n50_10000_walkers_vs_oracle(oracle):
+    """BASELINE configs[2]: N=50, 1e4 target walkers, capacity 1.25e4, dt=1e-3,
+    kappa=0.5 (Proc default) -- thirteen branching CTAs, the CUDA-graph block
+    path (no estimators, one rank)."""
+    from phd_qmclib_b200 import engine
+    p = golden('model_lat_n50.npz')['params']
+    nop, size = int(p[3]), float(p[4])
+    target, wmax, nts, dt, seed = 10000, 12500, 8, 1e-3, 77
+    ini = _ini(np.random.default_rng(50), target, nop, size)
+    st = oracle.DMCState(p, ini, wmax)
+    eng = engine.Engine(_spec(p))
+    dp = eng.dmc_params(dt, wmax, target, 0.5, seed, 0.0, size)
+    eng.dmc_init(dp, ini)
+    for _ in range(3):
+        a = st.run_block(seed, dt, target, 0.5, nts, 0.0, size)
+        b = eng.dmc_run_block(nts)
+        assert np.array_equal(a['num_walkers'], b['num_walkers'])
+        for k in ('energy', 'weight', 'ref_energy', 'accum_energy'):
+            assert rel_err(b[k], a[k]) < 1e-10, k
+    _check_state(eng, st)
+    eng.close()
+
+
+def test_dmc_config5_n200_estimators_vs_oracle(oracle):
+    """BASELINE configs[4] shape: N=200 deep lattice, 4096 target walkers,
+    S(k) with M=400 modes and density with B=6400 bins, both pure (forward
+    walking), estimator series of the second block against the oracle."""
+    from phd_qmclib_b200 import engine
+    p = golden('model_deep_n200.npz')['params']
+    nop, size = int(p[3]), float(p[4])
+    target, wmax, nts, dt, seed = 4096, 5120, 3, 1e-3, 5
+    modes, bins = 400, 6400
+    ini = _ini(np.random.default_rng(200), target, nop, size)
+    st = oracle.DMCState(p, ini, wmax)
+    ssf = dict(num=modes, pure=True, pfw=nts, iter=np.zeros((nts, modes, 3)),
+               aux=np.zeros((2, wmax, modes, 3)))
+    den = dict(num=bins, pure=True, pfw=nts, iter=np.zeros((nts, bins)),
+               aux=np.zeros((2, wmax, bins)))
+    eng = engine.Engine(_spec(p))
+    dp = eng.dmc_params(dt, wmax, target, 0.5, seed, 0.0, size,
+                        ssf=(modes, True, nts), density=(bins, True, nts))
+    eng.dmc_init(dp, ini)
+    for blk in range(2):
+        est = blk > 0
+        for d in (ssf, den):
+            d['iter'][:] = 0
+            d['aux'][:] = 0
+        a = st.run_block(seed, dt, target, 0.5, nts, 0.0, size, eval_est=est,
+                         ssf=ssf, density=den)
+        e_den, e_ssf = np.zeros((nts, bins)), np.zeros((nts, modes, 3))
+        b = eng.dmc_run_block(nts, eval_estimators=est, density=e_den,
+                              ssf=e_ssf)
+        assert np.array_equal(a['num_walkers'], b['num_walkers'])
+        for k in ('energy', 'weight', 'ref_energy', 'accum_energy'):
+            assert rel_err(b[k], a[k]) < 1e-10, k
+        if est:
+            assert np.allclose(e_den, den['iter'], rtol=1e-13, atol=1e-13)
+            assert np.max(np.abs(e_ssf - ssf['iter'])) \
+                < 1e-11 * np.max(np.abs(ssf['iter']))
+    eng.close()
+
+
+def test_branching_table_matches_serial_prefix_at_scale(oracle):
+    """The cloning table alone, at 1.5e5 slots (147 branching CTAs, the bench
+    shard): run one engine step from explicit weights and compare the whole
+    child->parent table with the oracle's serial loop on the same uniforms."""
+    from phd_qmclib_b200 import engine
+    from phd_qmclib_b200._lib import StateScalars
+    p = golden('model_ll_n16.npz')['params']
+    nop, size = int(p[3]), float(p[4])
+    n, wmax, seed = 125000, 150000, 4242
+    rng = np.random.default_rng(9)
+    confs = _ini(rng, n, nop, size)
+    eng = engine.Engine(_spec(p))
+    dp = eng.dmc_params(1e-3, wmax, n, 0.5, seed, 0.0, size)
+    ev = eng.model_eval(confs, want=('energy', 'drift'))
+    confs[:, 1] = ev['drift']
+    weight = np.exp(rng.normal(0.0, 0.35, size=n))
+    weight[::97] = 0.0                       # certain deaths
+    weight[5::1013] = 7.3                    # many children of one parent
+    sc = StateScalars()
+    sc.num_walkers, sc.max_num_walkers = n, wmax
+    sc.ref_energy = float(ev['energy'].mean())
+    sc.weight, sc.energy = float(n), float(ev['energy'].sum())
+    eng.dmc_set_state(dp, confs, ev['energy'], weight, sc)
+    b = eng.dmc_run_block(1)
+    s = eng.dmc_get_state()
+    # the oracle's serial loop on the same per-slot Philox uniforms
+    u = np.array([oracle.rng_uniform2(seed, i, 0, 0, 0)[0] for i in range(n)])
+    nw, ref = oracle.branch(weight, n, wmax, u)
+    assert int(b['num_walkers'][0]) == nw
+    assert np.array_equal(s['cloning_ref'][:nw], ref[:nw])
+    want_e = float(ev['energy'][ref[:nw]].sum())
+    assert abs(b['energy'][0] - want_e) < 1e-11 * abs(want_e)
+    eng.close()
