@@ -52,6 +52,18 @@ def scaled_err(a, b):
     return float(np.max(np.abs(a - b) / den))
 
 
+def conditioned_rel_err(a, b, floor=1e-2):
+    """Strict |a-b|/|b| over the entries that are not small by cancellation:
+    |b| >= floor * median|b|.  The few entries below the floor (a sum of
+    O(1e3) terms that lands within 1 % of zero) are bounded through
+    ``scaled_err``; no fp64 implementation, the reference included, holds a
+    relative error there."""
+    a, b = np.atleast_1d(a).astype(float), np.atleast_1d(b).astype(float)
+    keep = np.abs(b) >= floor * float(np.median(np.abs(b)))
+    assert keep.mean() > 0.97
+    return rel_err(a[keep], b[keep])
+
+
 @pytest.fixture(scope='session')
 def oracle():
     import oracle as _o

@@ -80,14 +80,15 @@ def test_dmc_n100_8192_walkers_vs_oracle(oracle, energy_mode):
     eng.close()
 
 
-@pytest.mark.parametrize('n_ini,wmax', [(3000, 3500), (2500, 2 * BR_TILE + 1),
+@pytest.mark.parametrize('n_ini,wmax', [(3000, 3500), (2040, 2 * BR_TILE + 1),
                                         (5000, 5 * BR_TILE)])
 def test_capacity_hit_inside_a_later_cta(oracle, n_ini, wmax):
     """Quirk Q8 (qmc_base/dmc.py:636-651): the reference fills slots in
     parent order and drops everything past the capacity.  A reference energy
-    far too low makes every step overflow; the cut falls among the parents of
-    branching CTA >= 2 (and, for wmax = 2049, one slot into the third tile of
-    children; for wmax = 5120 exactly on a tile boundary)."""
+    far too high for the first step makes the population overflow; the cut
+    falls among the parents of a branching CTA with index >= 1 or 2 (for
+    wmax = 2049 one slot into the third tile of children; for wmax = 5120
+    exactly on a tile boundary).  Compared step by step."""
     from phd_qmclib_b200 import engine
     p = golden('model_ll_n16.npz')['params']
     nop, size = int(p[3]), float(p[4])
@@ -96,16 +97,22 @@ def test_capacity_hit_inside_a_later_cta(oracle, n_ini, wmax):
     eng = engine.Engine(_spec(p))
     dp = eng.dmc_params(5e-3, wmax, n_ini, 0.0, 9, 0.0, size)
     eng.dmc_init(dp, ini, ref_energy=60.0)
-    a = st.run_block(9, 5e-3, n_ini, 0.0, 5, 0.0, size)
-    b = eng.dmc_run_block(5)
-    assert a['num_walkers'].max() == wmax
-    assert np.array_equal(a['num_walkers'], b['num_walkers'])
-    for k in ('energy', 'weight', 'ref_energy', 'accum_energy'):
-        assert rel_err(b[k], a[k]) < 1e-10, k
-    # the last parent that got a slot sits in a CTA with index >= 2
-    nw = st.num_walkers
-    assert nw == wmax
-    assert st.ref[nw - 1] >= 2 * BR_TILE or wmax == 2 * BR_TILE + 1
+    cut_parents = []
+    for _ in range(4):
+        a = st.run_block(9, 5e-3, n_ini, 0.0, 1, 0.0, size)
+        b = eng.dmc_run_block(1)
+        assert np.array_equal(a['num_walkers'], b['num_walkers'])
+        for k in ('energy', 'weight', 'ref_energy', 'accum_energy'):
+            assert rel_err(b[k], a[k]) < 1e-10, k
+        nw = st.num_walkers
+        s = eng.dmc_get_state()
+        assert np.array_equal(s['cloning_ref'][:nw], st.ref[:nw])
+        if nw == wmax:
+            cut_parents.append(int(st.ref[nw - 1]))
+    # the population did hit the capacity, and the last parent that got a
+    # slot sat in a later branching CTA
+    assert cut_parents and max(cut_parents) >= min(2 * BR_TILE, n_ini) - BR_TILE
+    assert max(cut_parents) // BR_TILE >= (2 if n_ini > 2 * BR_TILE else 1)
     assert eng.dmc_scalars().capacity_hits >= 1
     _check_state(eng, st)
     eng.close()

@@ -5,7 +5,8 @@ max-norm."""
 import numpy as np
 import pytest
 
-from conftest import golden, golden_names, maxnorm_err, rel_err, scaled_err
+from conftest import (conditioned_rel_err, golden, golden_names, maxnorm_err,
+                      rel_err, scaled_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -24,8 +25,9 @@ def test_model_eval_vs_reference(eng_mod, name):
     with eng_mod.Engine((g['params'][:12], g['params'][12:19],
                          g['params'][19:])) as eng:
         o = eng.model_eval(g['confs'])
-    assert scaled_err(o['lnpsi'], g['lnpsi']) < TOL
-    assert scaled_err(o['energy'], g['energy']) < TOL
+    # strict relative error against the live reference's values
+    assert rel_err(o['lnpsi'], g['lnpsi']) < TOL
+    assert rel_err(o['energy'], g['energy']) < TOL
     assert maxnorm_err(o['drift'], g['drift']) < TOL
 
 
@@ -42,8 +44,9 @@ def test_model_eval_vs_oracle_bulk(eng_mod, oracle, name, nconf):
     ref = oracle.model_eval(p, confs)
     with eng_mod.Engine((p[:12], p[12:19], p[19:])) as eng:
         o = eng.model_eval(confs)
-    assert scaled_err(o['lnpsi'], ref['lnpsi']) < TOL
-    assert scaled_err(o['energy'], ref['energy']) < TOL
+    for k in ('lnpsi', 'energy'):
+        assert conditioned_rel_err(o[k], ref[k]) < TOL, k
+        assert scaled_err(o[k], ref[k]) < TOL, k
     assert maxnorm_err(o['drift'], ref['drift']) < TOL
 
 
@@ -94,8 +97,8 @@ def test_physical_funcs_vs_reference(name):
     p = g['params']
     pf = model.PhysicalFuncs((p[:12], p[12:19], p[19:]))
     confs = g['confs']
-    assert scaled_err(pf.wf_abs_log(confs), g['lnpsi']) < TOL
-    assert scaled_err(pf.energy(confs), g['energy']) < TOL
+    assert rel_err(pf.wf_abs_log(confs), g['lnpsi']) < TOL
+    assert rel_err(pf.energy(confs), g['energy']) < TOL
     assert np.ndim(pf.energy(confs[0])) == 0
     nobd = g['obd'].shape[0]
     # (S,1) against (B,2,N) broadcasts to (S,B)
