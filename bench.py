@@ -1,26 +1,37 @@
 #!/usr/bin/env python
-"""Headline benchmark: DMC walker-steps/s of the mrbp_qmc hot path (N=100).
+"""Benchmark of the mrbp_qmc hot path on B200: walker-steps/s (DMC) or
+chain-steps/s (VMC).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--config c4|c3_dmc50|c5_est|c2_vmc]
 
-Workload (BASELINE.json configs[3], SURVEY.md 8d "C4"): multi-rods Bose gas,
-N = L = 100, V0 = 5 pi^2, g = 2, r_m = L/4, dt = 6.25e-4, 1.25e5 target
-walkers PER GPU (1e6 on 8 GPUs; capacity 1.25x), kappa = 0.5.  One bench
-"step" = one block of `nts` DMC time steps = one `next()` of the reference's
-`Sampling.blocks()` = one qmcb_dmc_run_block call.  Weak scaling: per-GPU
-population is fixed as N grows.
+Workloads (BASELINE.json `configs`):
+  c4        (default, the headline) configs[3]: DMC N = L = 100, V0 = 5 pi^2,
+            g = 2, r_m = L/4, dt = 6.25e-4, 1.25e5 target walkers PER GPU (1e6
+            on 8 GPUs; capacity 1.25x), kappa = 0.5, blocks of 128 time steps
+  c3_dmc50  configs[2]: DMC N = 50, 1e4 target walkers, dt = 1e-3, blocks of 512
+  c5_est    configs[4]: DMC N = 200 deep lattice (V0 = 20 pi^2), 3.125e4 target
+            walkers per GPU (2.5e5 on 8), dt = 1e-3, pure S(k) with M = 400 and
+            pure density with B = 6400 evaluated every step, blocks of 64
+  c2_vmc    configs[1]: VMC N = 50, 1e5 independent chains per GPU, energy and
+            S(k) (M = 50) estimators, blocks of 256 steps
+One bench "step" = one block = one `next()` of the reference's
+`Sampling.blocks()` = one qmcb_dmc_run_block / qmcb_vmc_run_block call.  Weak
+scaling: the per-GPU population is fixed as N grows.
 
-Lines printed (rank 0, one JSON object):
-  value  walker-steps/s of the whole job, walkers resident in HBM
+One JSON line on stdout (rank 0):
+  value  units/s of the whole job, population resident in HBM
   e2e    same metric through the C ABI with HOST buffers: every step copies
          the whole population host->device (pinned), runs the block, and
-         copies the evolved population and the per-step series back
-  roofline      the fused step kernel against the fp64 DFMA peak measured in
-                this run (MEASURED_PEAKS.json has no fp64 entry)
-  cpu_baseline  the oracle port of the reference algorithm on the host cores
+         copies the evolved population and the block's results back
+  roofline      the dominant kernel against the fp64 DFMA peak measured in
+                this run (MEASURED_PEAKS.json has no fp64 entry) and nominal
+  cpu_baseline  the reference's own Numba implementation on the host cores
+                (kind "reference"; the C port of oracle/ with an explicit
+                reason only when the reference cannot run)
 
-`--impl reference` times that oracle port alone (the reference is Python +
-Numba and does not exist on the GPU box).
+`--impl reference` times the reference (`mrbp_qmc.{dmc,vmc}.Sampling.blocks()`
+from baseline/_ref, through oracle/refshim.py) alone on the host cores.
 """
 import argparse
 import json
@@ -36,35 +47,79 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NOP = 100
-TIME_STEP = 6.25e-4
 NWC = 0.5
 CAP_FACTOR = 1.25
 SEED = 7
+PI2 = math.pi ** 2
+
+CONFIGS = {
+    'c4': dict(
+        kind='dmc', nop=100, v0=5 * PI2, g=2.0, dt=6.25e-4, walkers=125000,
+        nts=128, modes=0, bins=0, metric='dmc_walker_steps_per_sec',
+        unit='walker-steps/s', baseline_config='configs[3] shard',
+        ref=dict(nw=4096, nts=16)),
+    'c3_dmc50': dict(
+        kind='dmc', nop=50, v0=5 * PI2, g=2.0, dt=1e-3, walkers=10000,
+        nts=512, modes=0, bins=0, metric='dmc_walker_steps_per_sec',
+        unit='walker-steps/s', baseline_config='configs[2]',
+        ref=dict(nw=4096, nts=16)),
+    'c5_est': dict(
+        kind='dmc', nop=200, v0=20 * PI2, g=2.0, dt=1e-3, walkers=31250,
+        nts=64, modes=400, bins=6400, metric='dmc_walker_steps_per_sec',
+        unit='walker-steps/s', baseline_config='configs[4] shard',
+        ref=dict(nw=512, nts=4)),
+    'c2_vmc': dict(
+        kind='vmc', nop=50, v0=5 * PI2, g=4.0, chains=100000, ns=256,
+        modes=50, metric='vmc_chain_steps_per_sec', unit='chain-steps/s',
+        baseline_config='configs[1]', ref=dict(ns=4096)),
+}
 
 
 def flops_per_walker_step(n):
-    """Algorithmic work model of SURVEY.md 8(d)."""
+    """Algorithmic work model of SURVEY.md 8(d) (DMC step)."""
     return 58 * n * (n - 1) / 2 + 113 * n + 35
+
+
+def ssf_flops(n, m):
+    """S(k) per evaluated configuration."""
+    return n * (40 + 8 * m) + 3 * m
+
+
+def vmc_flops_per_chain_step(n, m, accept):
+    """Same convention for a VMC step: every step moves N
+    particles (8 flop each) and evaluates ln|Psi| (per unordered pair: 6 for
+    the distance and argument + 40 for the trigonometric function + 40 for
+    its logarithm; 90 per particle for ln f1); an accepted step adds E_L
+    (58 per pair + 50 per particle) and rho_k."""
+    pairs = n * (n - 1) / 2
+    return (8 * n + 86 * pairs + 90 * n
+            + accept * (58 * pairs + 50 * n + (ssf_flops(n, m) if m else 0)))
 
 
 def bytes_per_walker_step(n):
     return 32 * n + 32
 
 
-def model_spec():
+def spec_kwargs(cfg):
+    n = cfg['nop']
+    return dict(lattice_depth=cfg['v0'], lattice_ratio=1.0,
+                interaction_strength=cfg['g'], boson_number=n,
+                supercell_size=float(n), tbf_contact_cutoff=0.25 * n)
+
+
+def model_spec(cfg):
     from phd_qmclib_b200 import model
-    return model.Spec(5 * math.pi ** 2, 1, 2, NOP, NOP, 0.25 * NOP)
+    return model.Spec(**spec_kwargs(cfg))
 
 
-def initial_confs(nw, seed):
+def initial_confs(nw, nop, seed):
     """Walkers near the Mott-like ground state: one boson per lattice well
     (well = [0, 1/2) of each unit cell) with a small random offset, so the
     population equilibrates within the warm-up blocks."""
     rng = np.random.default_rng(seed)
-    ini = np.zeros((nw, 2, NOP))
-    ini[:, 0] = (np.arange(NOP)[None, :] + 0.25
-                 + 0.15 * (rng.random((nw, NOP)) - 0.5))
+    ini = np.zeros((nw, 2, nop))
+    ini[:, 0] = (np.arange(nop)[None, :] + 0.25
+                 + 0.15 * (rng.random((nw, nop)) - 0.5))
     return ini
 
 
@@ -133,59 +188,190 @@ class ClockSampler:
                 'reasons': sorted(reasons)}
 
 
+def workload_config(name, cfg, args, world):
+    n = cfg['nop']
+    if cfg['kind'] == 'vmc':
+        return {
+            'workload': f'mrbp_qmc VMC N={n} (BASELINE {cfg["baseline_config"]}'
+                        f'): V0={cfg["v0"] / PI2:g}pi^2 g={cfg["g"]:g} L={n} '
+                        f'r_m={n // 4} move_spread=0.25 well widths, energy + '
+                        f'S(k) M={cfg["modes"]} every step',
+            'bench_config': name, 'boson_number': n,
+            'chains_per_gpu': args.walkers,
+            'global_chains': args.walkers * world,
+            'steps_per_step': args.nts,
+            'parallelism': f'chains sharded over {world} GPU(s), no '
+                           f'collective',
+            'l2_policy': 'chain state lives in registers for the whole '
+                         'block; per-chain sums (%.0f MB) written once per '
+                         'block' % (args.walkers * (2 + 3 * cfg['modes']) * 8
+                                    / 1e6),
+        }
+    est = ('off in the timed region' if not (cfg['modes'] or cfg['bins']) else
+           f'pure S(k) M={cfg["modes"]} + pure density B={cfg["bins"]} '
+           f'every step, inside the timed region')
+    return {
+        'workload': f'mrbp_qmc DMC N={n} (BASELINE {cfg["baseline_config"]}): '
+                    f'V0={cfg["v0"] / PI2:g}pi^2 g={cfg["g"]:g} L={n} '
+                    f'r_m={n // 4} dt={cfg["dt"]:g} kappa={NWC}',
+        'bench_config': name, 'boson_number': n,
+        'target_walkers_per_gpu': args.walkers,
+        'capacity_per_gpu': int(args.walkers * CAP_FACTOR),
+        'global_target_walkers': args.walkers * world,
+        'time_steps_per_step': args.nts,
+        'estimators': est,
+        'parallelism': f'walkers sharded over {world} GPU(s)',
+        'l2_policy': ('working set (2 x %.0f MB walker buffers%s) %s the '
+                      '126 MB L2' % (
+                          args.walkers * CAP_FACTOR * 16 * n / 1e6,
+                          ' + %.0f MB S(k) rows' % (
+                              2 * args.walkers * CAP_FACTOR * 24
+                              * cfg['modes'] / 1e6) if cfg['modes'] else '',
+                          'exceeds' if args.walkers * CAP_FACTOR * 32 * n
+                          + 2 * args.walkers * CAP_FACTOR * 24 * cfg['modes']
+                          > 126e6 else 'fits (the configuration BASELINE '
+                          'names is this small); L2 flushed between timed '
+                          'blocks by a 256 MB memset: see l2_flush')),
+    }
+
+
 # ---------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference algorithm on the host cores
+# CPU arm: the reference's Numba implementation on the host cores; the C port
+# of oracle/ only as a fallback with an explicit reason
 # ---------------------------------------------------------------------------
-def cpu_port_walker_steps_per_s(budget_s=12.0, nw=4096, threads=None):
-    """Oracle DMC (OpenMP over walkers, like the reference's prange) on a
-    bounded sample of the bench workload.  Returns (value, cores, sample)."""
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+def _oracle_path():
+    p = os.path.join(ROOT, 'oracle')
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def cpu_port_units_per_s(cfg, budget_s=12.0, threads=None):
+    """Oracle port (OpenMP over walkers, like the reference's prange) on a
+    bounded sample of the workload.  Returns a cpu_baseline-shaped dict."""
+    _oracle_path()
     import oracle
     from phd_qmclib_b200 import model
     oracle.lib()
     cores = threads or os.cpu_count() or 1
     oracle.set_num_threads(cores)
-    p = model.param_block(model_spec())
+    p = model.param_block(model_spec(cfg))
+    n = cfg['nop']
+    if cfg['kind'] == 'vmc':
+        nch, ns = 4 * cores, 64
+        cur = initial_confs(nch, n, 0)
+        ln = oracle.model_eval(p, cur, want=('lnpsi',))['lnpsi']
+        spread = 0.25 * model_spec(cfg).well_width
+        eprev, sprev = np.zeros(nch), np.zeros((nch, cfg['modes'], 3))
+        oracle.vmc_block(p, 1, spread, 0.0, float(n), cur, ln, eprev, sprev,
+                         cfg['modes'], 2, 0, True)
+        t0 = time.perf_counter()
+        oracle.vmc_block(p, 1, spread, 0.0, float(n), cur, ln, eprev, sprev,
+                         cfg['modes'], ns, 1, False)
+        dt = time.perf_counter() - t0
+        return dict(value=nch * ns / dt, unit=cfg['unit'], cores=cores,
+                    kind='port', seconds=dt,
+                    sample=f'{nch} chains x {ns} steps, oracle/qmc_oracle.c '
+                           f'with OpenMP')
+    nw = cfg['ref']['nw']
     cap = int(nw * CAP_FACTOR)
-    st = oracle.DMCState(p, initial_confs(nw, 11), cap)
+    st = oracle.DMCState(p, initial_confs(nw, n, 11), cap)
     t0 = time.perf_counter()
-    it = st.run_block(SEED, TIME_STEP, nw, NWC, 1, 0.0, float(NOP))
+    it = st.run_block(SEED, cfg['dt'], nw, NWC, 1, 0.0, float(n))
     t1 = time.perf_counter() - t0
     nts = int(max(2, min(256, budget_s / max(t1, 1e-4))))
     t0 = time.perf_counter()
-    it = st.run_block(SEED, TIME_STEP, nw, NWC, nts, 0.0, float(NOP))
+    it = st.run_block(SEED, cfg['dt'], nw, NWC, nts, 0.0, float(n))
     dt = time.perf_counter() - t0
     ws = float(it['num_walkers'].sum())
-    sample = (f'{nw} target / {cap} capacity walkers x {nts} time steps of '
-              f'the bench workload, oracle/qmc_oracle.c with OpenMP')
-    return ws / dt, cores, sample, dt
+    return dict(value=ws / dt, unit=cfg['unit'], cores=cores, kind='port',
+                seconds=dt,
+                sample=f'{nw} target / {cap} capacity walkers x {nts} time '
+                       f'steps of the bench workload (estimators off), '
+                       f'oracle/qmc_oracle.c with OpenMP')
 
 
-def run_reference(args):
+def cpu_reference_units_per_s(cfg, budget_s=20.0, serial_too=False,
+                              max_blocks=6):
+    """The LIVE reference under oracle/refshim.py (protocol of SURVEY.md 8d /
+    BASELINE.md section 3).  Raises RuntimeError with the reason when the
+    reference cannot run here."""
+    _oracle_path()
+    import ref_arm
+    ok, why = ref_arm.probe()
+    if not ok:
+        raise RuntimeError(why)
+    n = cfg['nop']
+    kw = spec_kwargs(cfg)
+    if cfg['kind'] == 'vmc':
+        from phd_qmclib_b200 import model
+        r = ref_arm.vmc_chain_steps_per_s(
+            kw, move_spread=0.25 * model.Spec(**kw).well_width,
+            ns=cfg['ref']['ns'], num_modes=cfg['modes'], budget_s=budget_s,
+            max_blocks=max_blocks)
+    else:
+        nw = cfg['ref']['nw']
+        common = dict(nw=nw, cap=int(nw * CAP_FACTOR), dt=cfg['dt'], nwc=NWC,
+                      nts=cfg['ref']['nts'], num_modes=cfg['modes'],
+                      num_bins=cfg['bins'], max_blocks=max_blocks)
+        r = ref_arm.dmc_walker_steps_per_s(kw, parallel=True,
+                                           budget_s=budget_s, **common)
+        if serial_too:
+            common.update(nw=max(64, nw // 8), cap=int(max(64, nw // 8)
+                                                       * CAP_FACTOR))
+            s = ref_arm.dmc_walker_steps_per_s(kw, parallel=False,
+                                               budget_s=budget_s / 2,
+                                               **common)
+            r['serial'] = dict(value=s['value'], cores=1, sample=s['sample'])
+    r.update(unit=cfg['unit'], kind='reference', cpu_model=ref_arm.cpu_model(),
+             host_cores=os.cpu_count())
+    return r
+
+
+def cpu_baseline(cfg, serial_too=False, budget_s=20.0, max_blocks=6):
+    """kind "reference" when the Numba reference runs here, else the port
+    with the reason it was used."""
+    try:
+        return cpu_reference_units_per_s(cfg, budget_s=budget_s,
+                                         serial_too=serial_too,
+                                         max_blocks=max_blocks)
+    except Exception as exc:       # noqa: BLE001 - any failure is a reason
+        r = cpu_port_units_per_s(cfg)
+        r['reason'] = ('reference (Numba) arm unavailable: '
+                       f'{exc.__class__.__name__}: {exc}'[:400])
+        return r
+
+
+def run_reference(name, cfg, args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
     per_step = []
-    sample = ''
-    # each "step" is a bounded sample sized to keep the whole run short
-    budget = max(1.5, min(10.0, 100.0 / max(1, args.steps + args.warmup)))
-    for i in range(args.warmup + args.steps):
-        v, cores, sample, dt = cpu_port_walker_steps_per_s(budget_s=budget)
+    last = None
+    # each "step" is a bounded sample sized to keep the whole run short; the
+    # JIT compilation of the reference (~1-2 min) happens once, in step 0
+    total = max(1, args.steps + args.warmup)
+    budget = max(2.0, min(12.0, 90.0 / total))
+    for i in range(total):
+        r = cpu_baseline(cfg, serial_too=(i == total - 1), budget_s=budget,
+                         max_blocks=3)
         if i >= args.warmup:
-            per_step.append((v, dt))
+            per_step.append((r['value'], r['seconds']))
+            last = r
     value = float(np.mean([v for v, _ in per_step]))
     ms = float(np.mean([d for _, d in per_step])) * 1e3
+    cb = {k: last[k] for k in ('unit', 'cores', 'kind', 'sample',
+                               'threading_layer', 'numba', 'cpu_model',
+                               'host_cores', 'serial', 'reason') if k in last}
+    cb['value'] = value
     line = {
-        'impl': 'reference', 'metric': 'dmc_walker_steps_per_sec',
-        'value': value, 'unit': 'walker-steps/s', 'n_gpus': args.gpus,
+        'impl': 'reference', 'metric': cfg['metric'],
+        'value': value, 'unit': cfg['unit'], 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(args, 1),
-        'cpu_baseline': {'value': value, 'unit': 'walker-steps/s',
-                         'cores': cores, 'kind': 'port', 'sample': sample},
-        'e2e': {'value': value, 'unit': 'walker-steps/s',
+        'config': workload_config(name, cfg, args, 1),
+        'cpu_baseline': cb,
+        'e2e': {'value': value, 'unit': cfg['unit'],
                 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -193,73 +379,134 @@ def run_reference(args):
     return 0
 
 
-def workload_config(args, world):
-    return {
-        'workload': 'mrbp_qmc DMC N=100 (BASELINE configs[3] shard): '
-                    'V0=5pi^2 g=2 L=100 r_m=25 dt=6.25e-4 kappa=0.5',
-        'boson_number': NOP,
-        'target_walkers_per_gpu': args.walkers,
-        'capacity_per_gpu': int(args.walkers * CAP_FACTOR),
-        'global_target_walkers': args.walkers * world,
-        'time_steps_per_step': args.nts,
-        'estimators': 'off in the timed region',
-        'parallelism': f'walkers sharded over {world} GPU(s)',
-        'l2_policy': 'working set (2 x %.0f MB walker buffers) exceeds the '
-                     '126 MB L2' % (args.walkers * CAP_FACTOR * 16 * NOP
-                                    / 1e6),
-    }
+def cpu_baseline_subprocess(name):
+    """The cpu_baseline leg of the GPU arm runs the reference arm in a child
+    process (its own OpenMP/Numba thread pools, none of torch's) and takes
+    the cpu_baseline object of its line."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference',
+           '--config', name, '--steps', '1', '--warmup', '0']
+    env = {k: v for k, v in os.environ.items()
+           if k not in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE')}
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, env=env,
+                             timeout=900)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith('{'):
+                return json.loads(ln)['cpu_baseline']
+        return {'value': None, 'kind': 'unavailable',
+                'reason': (out.stderr or 'no output')[-300:]}
+    except Exception as exc:       # noqa: BLE001
+        return {'value': None, 'kind': 'unavailable', 'reason': str(exc)}
 
 
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
-def run_b200(args):
+class Dist:
+    """torch.distributed plumbing of the bench (barrier, max/sum over ranks)."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py: no CUDA device (there is no CPU '
+                             'fallback for the product arm; use --impl '
+                             'reference)')
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            dist.init_process_group(
+                'nccl', device_id=torch.device('cuda', self.local))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def _red(self, x, op):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device='cuda')
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, x):
+        return self._red(x, self.dist.ReduceOp.MAX) if self.dist else x
+
+    def sum(self, x):
+        return self._red(x, self.dist.ReduceOp.SUM) if self.dist else x
+
+    def gather(self, x):
+        if self.dist is None:
+            return [x]
+        t = self.torch.zeros(self.world, dtype=self.torch.float64,
+                             device='cuda')
+        t[self.rank] = x
+        self.dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        return {}
+
+
+NOMINAL_FP64_TF = 148 * 64 * 2 * 1.965e9 / 1e12    # 37.2
+
+
+def roofline_fp64(kernel, ach_tf, peak_sust, peak_burst, extra):
+    r = {
+        'kernel': kernel, 'bound': 'fp64', 'achieved': ach_tf,
+        'peak': peak_sust, 'unit': 'TFLOP/s', 'frac': ach_tf / peak_sust,
+        'peak_source': 'DFMA microbenchmark measured in this run, sustained '
+                       '1.5 s (MEASURED_PEAKS.json has no fp64 figure)',
+        'peak_burst': peak_burst, 'frac_of_burst': ach_tf / peak_burst,
+        'peak_nominal': NOMINAL_FP64_TF,
+        'frac_of_nominal': ach_tf / NOMINAL_FP64_TF,
+    }
+    r.update(extra)
+    return r
+
+
+def committed_ncu_view(name):
+    """Executed-instruction view of the dominant kernel from the committed
+    ncu capture of this config (not measured in this run)."""
+    path = os.path.join(ROOT, 'profiles', 'kernel_ncu_view.json')
+    try:
+        return json.load(open(path)).get(name)
+    except Exception:
+        return None
+
+
+def run_dmc(name, cfg, args, D):
     import torch
-    import torch.distributed as dist
     from phd_qmclib_b200 import engine, _lib
-
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py: no CUDA device (there is no CPU fallback '
-                         'for the product arm; use --impl reference)')
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        # stdout carries exactly one JSON line: at NCCL_DEBUG=VERSION (the
-        # setting of the GPU boxes) NCCL prints its version banner there
-        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
-            del os.environ['NCCL_DEBUG']
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
+    world, rank, local = D.world, D.rank, D.local
+    n = cfg['nop']
     nw, nts = args.walkers, args.nts
     cap = int(nw * CAP_FACTOR)
-    spec = model_spec()
+    M, NB = cfg['modes'], cfg['bins']
+    est = bool(M or NB)
+    spec = model_spec(cfg)
     eng = engine.Engine(spec, device=local)
-    dp = eng.dmc_params(TIME_STEP, cap * world, nw * world, NWC, SEED, 0.0,
-                        float(NOP), local_capacity=cap)
+    dp = eng.dmc_params(cfg['dt'], cap * world, nw * world, NWC, SEED, 0.0,
+                        float(n), local_capacity=cap,
+                        ssf=(M, True, nts) if M else None,
+                        density=(NB, True, nts) if NB else None)
     if world > 1:
-        eng.comm_init_torch(dist, rank, world)
-    eng.dmc_init(dp, initial_confs(nw, 100 + rank),
+        eng.comm_init_torch(D.dist, rank, world)
+    eng.dmc_init(dp, initial_confs(nw, n, 100 + rank),
                  global_slot_offset=rank * cap)
     stream = torch.cuda.ExternalStream(eng.stream)
 
@@ -267,98 +514,103 @@ def run_b200(args):
     peak_burst = engine.measure_fp64_peak(local)
     peak_sust = engine.measure_fp64_peak(local, sustained_seconds=1.5)
 
+    # small working sets (c3_dmc50: 2 x 10 MB) would stay L2-resident between
+    # blocks: flush with a buffer larger than L2 between timed blocks
+    ws_bytes = cap * 32 * n + 2 * cap * 24 * M
+    flush = None
+    if ws_bytes <= 126e6:
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8,
+                            device='cuda')
+
+    den = np.zeros((nts, NB)) if NB else None
+    ssf = np.zeros((nts, M, 3)) if M else None
+    series = dict(energy=np.zeros(nts), weight=np.zeros(nts),
+                  num_walkers=np.zeros(nts, dtype=np.uint64),
+                  ref_energy=np.zeros(nts), accum_energy=np.zeros(nts))
+
+    def block():
+        eng.dmc_run_block(nts, eval_estimators=est, out=series, density=den,
+                          ssf=ssf)
+
     # ---- device-resident timing ------------------------------------------
     eng.set_profiling(True)
     moved = 0
     for _ in range(args.warmup):
-        eng.dmc_advance(nts)
+        block()
         if world > 1:
             eng.dmc_rebalance()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    D.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ws_total, kern_ms, launches, dev_ms = 0.0, 0.0, 0, 0.0
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
-    barrier(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    e0.record(stream)
-    ws_local, kern_ms, launches = 0.0, 0.0, 0
-    series = dict(energy=np.zeros(nts), weight=np.zeros(nts),
-                  num_walkers=np.zeros(nts, dtype=np.uint64),
-                  ref_energy=np.zeros(nts), accum_energy=np.zeros(nts))
-    local_ws_list = []
+    if flush is None:
+        e0.record(stream)
     for _ in range(args.steps):
-        eng.dmc_run_block(nts, out=series)
+        if flush is not None:
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            e0.record(stream)
+        block()
         st = eng.last_block_stats()
         kern_ms += st['step_kernel_ms']
         launches += st['launches']
-        local_ws_list.append(st.get('local_walker_steps', 0))
-        ws_local += float(series['num_walkers'].sum())   # GLOBAL when world>1
+        ws_total += float(series['num_walkers'].sum())   # GLOBAL if world > 1
         if world > 1:
             # order-preserving neighbour shifts, once per block, timed
             moved += eng.dmc_rebalance()
-    e1.record(stream)
-    barrier(); torch.cuda.synchronize()
+        if flush is not None:
+            e1.record(stream)
+            torch.cuda.synchronize()
+            dev_ms += e0.elapsed_time(e1)
+    if flush is None:
+        e1.record(stream)
+    D.barrier(); torch.cuda.synchronize()
     t1 = time.perf_counter()
-    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    if flush is None:
+        dev_ms = e0.elapsed_time(e1)
+    local_ms = dev_ms
+    dev_ms = D.max(dev_ms)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    # with several ranks the series already hold global counts
-    ws_total = ws_local
     value = ws_total / (dev_ms * 1e-3)
     ms_per_step = dev_ms / args.steps
-    e_per_particle = float(series['energy'][-1] / series['weight'][-1] / NOP)
+    e_per_particle = float(series['energy'][-1] / series['weight'][-1] / n)
+    n_local = float(eng.dmc_scalars().num_walkers)
+    per_rank = {'walkers': D.gather(n_local),
+                'step_kernel_ms_per_launch': D.gather(
+                    kern_ms / (args.steps * nts)),
+                'block_ms': D.gather(local_ms / args.steps)}
 
     # roofline of the step kernel (this rank's launches, this rank's walkers)
     ws_rank = ws_total / world
-    F = flops_per_walker_step(NOP)
+    F = flops_per_walker_step(n)
     ach_tf = ws_rank * F / (kern_ms * 1e-3) / 1e12
-    hbm_gbs = ws_rank * bytes_per_walker_step(NOP) / (kern_ms * 1e-3) / 1e9
-    traffic, ncu_view = None, None
-    prof_path = os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')
-    if os.path.exists(prof_path):
-        try:
-            tj = json.load(open(prof_path))
-            traffic = tj['dram_bytes_per_walker'] * ws_rank / (
-                args.steps * nts)
-            # the executed-instruction view of the same kernel, from the
-            # committed ncu capture (not measured in this run)
-            ncu_view = {k: tj[k] for k in (
-                'fp64_pipe_active_pct', 'issue_active_pct',
-                'warp_instructions_per_launch', 'registers_per_thread',
-                'source') if k in tj}
-        except Exception:
-            traffic = None
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
-    roofline = {
-        'kernel': 'dmc_step_kernel', 'bound': 'fp64',
-        'achieved': ach_tf, 'peak': peak_sust, 'unit': 'TFLOP/s',
-        'frac': ach_tf / peak_sust,
-        'peak_source': 'DFMA microbenchmark measured in this run, sustained '
-                       '1.5 s (MEASURED_PEAKS.json has no fp64 figure; '
-                       'nominal 37.2)',
-        'peak_burst': peak_burst, 'frac_of_burst': ach_tf / peak_burst,
+    hbm_gbs = ws_rank * bytes_per_walker_step(n) / (kern_ms * 1e-3) / 1e9
+    view = committed_ncu_view(name) or {}
+    traffic = None
+    if view.get('dram_bytes_per_walker') is not None:
+        traffic = view['dram_bytes_per_walker'] * ws_rank / (args.steps * nts)
+    peaks = measured_peaks()
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    roofline = roofline_fp64('dmc_step_kernel', ach_tf, peak_sust, peak_burst, {
         'flop_per_walker_step': F,
         'avg_launch_ms': kern_ms / (args.steps * nts),
-        'step_kernel_share_of_step': kern_ms / max_over_ranks(
-            e0.elapsed_time(e1)),
-        'traffic': traffic,
-        'ncu': ncu_view,
-        'hbm': {'achieved': hbm_gbs, 'peak': peaks.get('hbm_gbs', 6650.0),
-                'unit': 'GB/s',
-                'frac': hbm_gbs / peaks.get('hbm_gbs', 6650.0),
-                'bytes_per_walker_step': bytes_per_walker_step(NOP)},
-    }
+        'step_kernel_share_of_step': kern_ms / dev_ms,
+        'traffic': traffic, 'ncu': view or None,
+        'hbm': {'achieved': hbm_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': hbm_gbs / hbm_peak,
+                'bytes_per_walker_step': bytes_per_walker_step(n)},
+    })
 
     # ---- end to end through the C ABI with host buffers -------------------
     eng.set_profiling(False)
     nx = eng.dmc_get_next()
     n_live = int(nx['scalars'].num_walkers)
-    h_confs = engine.pinned_empty((cap, 2, NOP))
+    h_confs = engine.pinned_empty((cap, 2, n))
     h_energy = engine.pinned_empty((cap,))
     h_weight = engine.pinned_empty((cap,))
     h_slot = engine.pinned_empty((cap,))
@@ -367,63 +619,162 @@ def run_b200(args):
     sc = nx['scalars']
     h2d = d2h = 0
     e2e_ws = 0.0
+    est_bytes = nts * (3 * M + NB) * 8
 
     def e2e_step(sc, n_live):
         eng.dmc_set_state(dp, h_confs[:n_live], h_energy[:n_live],
                           h_weight[:n_live], sc, slot_energy=h_slot,
                           global_slot_offset=rank * cap)
-        eng.dmc_run_block(nts, out=series)
+        block()
         if world > 1:
             eng.dmc_rebalance()
         sc2 = eng.dmc_get_next_into(h_confs, h_energy, h_weight, h_slot)
         return sc2, int(sc2.num_walkers)
 
     sc, n_live = e2e_step(sc, n_live)        # warm-up
-    barrier(); torch.cuda.synchronize()
-    e0.record(stream)
+    D.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         n_in = n_live
         sc, n_live = e2e_step(sc, n_live)
-        h2d += n_in * (2 * NOP + 2) * 8 + cap * 8
-        d2h += n_live * (2 * NOP + 2) * 8 + cap * 8 + nts * 5 * 8
+        h2d += n_in * (2 * n + 2) * 8 + cap * 8
+        d2h += n_live * (2 * n + 2) * 8 + cap * 8 + nts * 5 * 8 + est_bytes
         e2e_ws += float(series['num_walkers'].sum())
-    e1.record(stream)
-    barrier(); torch.cuda.synchronize()
-    e2e_wall = max_over_ranks(time.perf_counter() - t0)
-    e2e = {'value': e2e_ws / e2e_wall, 'unit': 'walker-steps/s',
-           'h2d_bytes_per_step': int(sum_over_ranks(h2d) / args.steps),
-           'd2h_bytes_per_step': int(sum_over_ranks(d2h) / args.steps),
+    D.barrier(); torch.cuda.synchronize()
+    e2e_wall = D.max(time.perf_counter() - t0)
+    e2e = {'value': e2e_ws / e2e_wall, 'unit': cfg['unit'],
+           'h2d_bytes_per_step': int(D.sum(h2d) / args.steps),
+           'd2h_bytes_per_step': int(D.sum(d2h) / args.steps),
            'timing': 'host wall clock around K x (set_state from pinned '
                      'host + run_block + get_next to pinned host), max over '
                      'ranks',
            'ms_per_step': e2e_wall * 1e3 / args.steps}
-
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        v, cores, sample, _ = cpu_port_walker_steps_per_s()
-        cpu_baseline = {'value': v, 'unit': 'walker-steps/s', 'cores': cores,
-                        'kind': 'port', 'sample': sample}
-
-    if rank == 0:
-        line = {
-            'metric': 'dmc_walker_steps_per_sec', 'value': value,
-            'unit': 'walker-steps/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms_per_step,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f64', 'data': 'synthetic',
-            'config': workload_config(args, world),
-            'per_gpu_value': value / world,
-            'energy_per_particle_last_step': e_per_particle,
-            'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e,
-            'gpu_launches': int(launches), 'clocks': clocks,
-            'rebalanced_walkers_rank0': int(moved),
-            'lib': os.path.relpath(_lib.LIB_PATH, ROOT),
-        }
-        print(json.dumps(line), flush=True)
+    hits = int(eng.dmc_scalars().capacity_hits)
     eng.close()
-    if world > 1:
-        dist.destroy_process_group()
+    if rank != 0:
+        return None
+    return {
+        'metric': cfg['metric'], 'value': value, 'unit': cfg['unit'],
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': workload_config(name, cfg, args, world),
+        'per_gpu_value': value / world,
+        'energy_per_particle_last_step': e_per_particle,
+        'roofline': roofline, 'e2e': e2e, 'gpu_launches': int(launches),
+        'clocks': clocks, 'per_rank': per_rank,
+        'rebalanced_walkers_rank0': int(moved), 'capacity_hits_rank0': hits,
+        'l2_flush': flush is not None,
+        'lib': os.path.relpath(_lib.LIB_PATH, ROOT),
+    }
+
+
+def run_vmc(name, cfg, args, D):
+    import torch
+    from phd_qmclib_b200 import engine, _lib
+    world, rank, local = D.world, D.rank, D.local
+    n, M = cfg['nop'], cfg['modes']
+    nch, ns = args.walkers, args.nts
+    spec = model_spec(cfg)
+    spread = 0.25 * spec.well_width
+    eng = engine.Engine(spec, device=local)
+    ini = initial_confs(nch, n, 200 + rank)
+    eng.vmc_init(ini, spread, 1, 0.0, float(n), ssf_num_modes=M,
+                 chain_offset=rank * nch)
+    stream = torch.cuda.ExternalStream(eng.stream)
+    peak_burst = engine.measure_fp64_peak(local)
+    peak_sust = engine.measure_fp64_peak(local, sustained_seconds=1.5)
+
+    for _ in range(args.warmup):
+        eng.vmc_run_block(ns, series=False, sums=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    D.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    kern_ms, acc, esum = 0.0, 0.0, 0.0
+    for _ in range(args.steps):
+        o = eng.vmc_run_block(ns, series=False, sums=True)
+        kern_ms += eng.last_block_stats()['total_ms']
+        acc += float(o['accept_rate'].mean())
+        esum = float(o['sum_energy'][:, 0].mean() / ns / n)
+    e1.record(stream)
+    D.barrier(); torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    dev_ms = D.max(e0.elapsed_time(e1))
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    units = float(nch) * ns * args.steps * world
+    value = units / (dev_ms * 1e-3)
+    acc /= args.steps
+    F = vmc_flops_per_chain_step(n, M, acc)
+    ach_tf = (units / world) * F / (kern_ms * 1e-3) / 1e12
+    roofline = roofline_fp64('vmc_block_kernel', ach_tf, peak_sust,
+                             peak_burst, {
+        'flop_per_chain_step': F, 'accept_rate': acc,
+        'avg_launch_ms': kern_ms / args.steps,
+        'kernel_share_of_step': kern_ms / dev_ms,
+        'traffic': None, 'ncu': committed_ncu_view(name),
+    })
+
+    # ---- end to end: chains from host, block, per-chain sums to host ------
+    confs, _ = eng.vmc_get_state()
+    h_confs = engine.pinned_empty((nch, 2, n))
+    h_confs[:] = confs
+
+    def e2e_step():
+        eng.vmc_init(h_confs, spread, 1, 0.0, float(n), ssf_num_modes=M,
+                     chain_offset=rank * nch)
+        o = eng.vmc_run_block(ns, series=False, sums=True)
+        c2, _ = eng.vmc_get_state()
+        h_confs[:] = c2
+        return o
+
+    e2e_step()
+    D.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    D.barrier(); torch.cuda.synchronize()
+    wall = D.max(time.perf_counter() - t0)
+    h2d = nch * 2 * n * 8
+    d2h = nch * (2 * n + 1) * 8 + nch * (1 + 2 + 3 * M) * 8
+    e2e = {'value': units / wall, 'unit': cfg['unit'],
+           'h2d_bytes_per_step': int(h2d * world),
+           'd2h_bytes_per_step': int(d2h * world),
+           'timing': 'host wall clock around K x (vmc_init from pinned host '
+                     '+ run_block with per-chain sums to host + get_state), '
+                     'max over ranks; the first step of a re-initialised '
+                     'block re-evaluates the initial configuration',
+           'ms_per_step': wall * 1e3 / args.steps}
+    eng.close()
+    if rank != 0:
+        return None
+    return {
+        'metric': cfg['metric'], 'value': value, 'unit': cfg['unit'],
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': workload_config(name, cfg, args, world),
+        'per_gpu_value': value / world,
+        'energy_per_particle_last_block': esum, 'accept_rate': acc,
+        'roofline': roofline, 'e2e': e2e, 'gpu_launches': int(args.steps),
+        'clocks': clocks, 'lib': os.path.relpath(_lib.LIB_PATH, ROOT),
+    }
+
+
+def run_b200(name, cfg, args):
+    D = Dist()
+    line = (run_vmc if cfg['kind'] == 'vmc' else run_dmc)(name, cfg, args, D)
+    if D.rank == 0:
+        line['cpu_baseline'] = None
+        if D.world == 1 and not args.no_cpu:
+            line['cpu_baseline'] = cpu_baseline_subprocess(name)
+        print(json.dumps(line), flush=True)
+    D.close()
     return 0
 
 
@@ -433,15 +784,21 @@ def main():
     ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--walkers', type=int, default=125000,
-                    help='target walkers per GPU')
-    ap.add_argument('--nts', type=int, default=128,
-                    help='DMC time steps per bench step (block)')
+    ap.add_argument('--config', default='c4', choices=sorted(CONFIGS))
+    ap.add_argument('--walkers', type=int, default=None,
+                    help='target walkers (chains) per GPU')
+    ap.add_argument('--nts', type=int, default=None,
+                    help='time steps per bench step (block)')
     ap.add_argument('--no-cpu', action='store_true',
                     help='skip the cpu_baseline leg')
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.walkers is None:
+        args.walkers = cfg.get('walkers', cfg.get('chains'))
+    if args.nts is None:
+        args.nts = cfg.get('nts', cfg.get('ns'))
     if args.impl == 'reference':
-        return run_reference(args)
+        return run_reference(args.config, cfg, args)
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.gpus != world and args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun
@@ -450,7 +807,7 @@ def main():
                '--master-port', '29511', os.path.abspath(__file__)] \
             + sys.argv[1:]
         return subprocess.call(cmd)
-    return run_b200(args)
+    return run_b200(args.config, cfg, args)
 
 
 if __name__ == '__main__':

@@ -57,7 +57,8 @@ def lib():
     L.qmco_one_body_density.restype = None
     L.qmco_rng_uniform2.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32,
                                     C.c_uint32, C.c_uint32, _f64p]
-    L.qmco_rng_normal2.argtypes = L.qmco_rng_uniform2.argtypes
+    L.qmco_rng_normal4.argtypes = L.qmco_rng_uniform2.argtypes
+    L.qmco_rng_uniform4.argtypes = L.qmco_rng_uniform2.argtypes
     L.qmco_branch.argtypes = [_f64p, C.c_int64, C.c_int64, _f64p, _i64p]
     L.qmco_branch.restype = C.c_int64
     L.qmco_evolve_state.argtypes = [
@@ -238,9 +239,15 @@ def rng_uniform2(seed, c0, c1, c2, stream):
     return out
 
 
-def rng_normal2(seed, c0, c1, c2, stream):
-    out = np.empty(2)
-    lib().qmco_rng_normal2(seed, c0, c1, c2, stream, out)
+def rng_normal4(seed, c0, c1, c2, stream):
+    out = np.empty(4)
+    lib().qmco_rng_normal4(seed, c0, c1, c2, stream, out)
+    return out
+
+
+def rng_uniform4(seed, c0, c1, c2, stream):
+    out = np.empty(4)
+    lib().qmco_rng_uniform4(seed, c0, c1, c2, stream, out)
     return out
 
 

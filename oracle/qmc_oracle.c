@@ -380,13 +380,17 @@ QMCO_API void qmco_one_body_density(const double *p, const double *confs,
 /*   counter = (c0, c1, c2, stream):                                   */
 /*     stream 0  DMC branching   c0 = global slot, c1 = 0, c2 = step   */
 /*     stream 1  DMC diffusion   c0 = global slot, c1 = q,  c2 = step  */
-/*               -> normals for particles 2q and 2q+1                  */
+/*               -> normals for particles 4q .. 4q+3                   */
 /*     stream 2  VMC proposal    c0 = chain, c1 = q, c2 = step         */
-/*               -> uniforms for particles 2q and 2q+1                 */
+/*               -> uniforms / normals for particles 4q .. 4q+3        */
 /*     stream 3  VMC acceptance  c0 = chain, c1 = 0, c2 = step         */
-/*   uniform  u = ((x0 << 21) ^ (x1 >> 11)) * 2^-53        in [0, 1)   */
-/*   normals  (Box-Muller) r = sqrt(-2 ln(u1 + 2^-53)),                */
-/*            (n0, n1) = r * (cos, sin)(2 pi u2)                       */
+/*   streams 0, 3 (one draw per call, 53 bits):                        */
+/*     uniform  u = ((x0 << 21) ^ (x1 >> 11)) * 2^-53      in [0, 1)   */
+/*   streams 1, 2 (four draws per call, 32 bits each):                 */
+/*     uniform  u_i = (x_i + 1/2) 2^-32                    in (0, 1)   */
+/*     normals  (Box-Muller) r_a = sqrt(-2 ln((x0 + 1/2) 2^-32)),      */
+/*              (n0, n1) = r_a (cos, sin)(2 pi x1 2^-32),              */
+/*              (n2, n3) likewise from x2, x3                          */
 /* ------------------------------------------------------------------ */
 static inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
 {
@@ -418,16 +422,30 @@ static inline void rng_uniform2(uint64_t seed, uint32_t c0, uint32_t c1,
     *u1 = u53(c[2], c[3]);
 }
 
-static inline void rng_normal2(uint64_t seed, uint32_t c0, uint32_t c1,
-                               uint32_t c2, uint32_t stream, double *n0,
-                               double *n1)
+static inline double u32_open(uint32_t x)
 {
-    double u0, u1;
-    rng_uniform2(seed, c0, c1, c2, stream, &u0, &u1);
-    double r = sqrt(-2.0 * log(u0 + 1.0 / 9007199254740992.0));
-    double th = 2.0 * M_PI * u1;
-    *n0 = r * cos(th);
-    *n1 = r * sin(th);
+    return ((double) x + 0.5) * (1.0 / 4294967296.0);
+}
+
+static inline void rng_uniform4(uint64_t seed, uint32_t c0, uint32_t c1,
+                                uint32_t c2, uint32_t stream, double u[4])
+{
+    uint32_t c[4] = {c0, c1, c2, stream};
+    philox4x32_10(c, (uint32_t) seed, (uint32_t) (seed >> 32));
+    for (int i = 0; i < 4; ++i) u[i] = u32_open(c[i]);
+}
+
+static inline void rng_normal4(uint64_t seed, uint32_t c0, uint32_t c1,
+                               uint32_t c2, uint32_t stream, double n[4])
+{
+    uint32_t c[4] = {c0, c1, c2, stream};
+    philox4x32_10(c, (uint32_t) seed, (uint32_t) (seed >> 32));
+    for (int h = 0; h < 2; ++h) {
+        double r = sqrt(-2.0 * log(u32_open(c[2 * h])));
+        double th = 2.0 * M_PI * ((double) c[2 * h + 1] * (1.0 / 4294967296.0));
+        n[2 * h] = r * cos(th);
+        n[2 * h + 1] = r * sin(th);
+    }
 }
 
 /* Expose the raw streams so tests can feed identical numbers elsewhere. */
@@ -437,10 +455,16 @@ QMCO_API void qmco_rng_uniform2(uint64_t seed, uint32_t c0, uint32_t c1,
     rng_uniform2(seed, c0, c1, c2, stream, out, out + 1);
 }
 
-QMCO_API void qmco_rng_normal2(uint64_t seed, uint32_t c0, uint32_t c1,
+QMCO_API void qmco_rng_normal4(uint64_t seed, uint32_t c0, uint32_t c1,
                                uint32_t c2, uint32_t stream, double *out)
 {
-    rng_normal2(seed, c0, c1, c2, stream, out, out + 1);
+    rng_normal4(seed, c0, c1, c2, stream, out);
+}
+
+QMCO_API void qmco_rng_uniform4(uint64_t seed, uint32_t c0, uint32_t c1,
+                                uint32_t c2, uint32_t stream, double *out)
+{
+    rng_uniform4(seed, c0, c1, c2, stream, out);
 }
 
 /* ------------------------------------------------------------------ */
@@ -713,19 +737,19 @@ QMCO_API void qmco_dmc_block(const double *p, uint64_t seed,
                                  unif, cloning_ref);
 #pragma omp parallel for schedule(static)
         for (int64_t s = 0; s < nw; ++s) {
-            for (int q = 0; 2 * q < nop; ++q) {
-                double n0, n1 = 0.;
+            for (int q = 0; 4 * q < nop; ++q) {
+                double n4[4] = {0., 0., 0., 0.};
                 if (normals_ext) {
                     const double *ne = normals_ext
                         + (step * max_num_walkers + s) * nop;
-                    n0 = ne[2 * q];
-                    if (2 * q + 1 < nop) n1 = ne[2 * q + 1];
+                    for (int i = 0; i < 4 && 4 * q + i < nop; ++i)
+                        n4[i] = ne[4 * q + i];
                 } else {
-                    rng_normal2(seed, (uint32_t) s, (uint32_t) q,
-                                (uint32_t) gstep, 1u, &n0, &n1);
+                    rng_normal4(seed, (uint32_t) s, (uint32_t) q,
+                                (uint32_t) gstep, 1u, n4);
                 }
-                normals[s * nop + 2 * q] = sigma * n0;
-                if (2 * q + 1 < nop) normals[s * nop + 2 * q + 1] = sigma * n1;
+                for (int i = 0; i < 4 && 4 * q + i < nop; ++i)
+                    normals[s * nop + 4 * q + i] = sigma * n4[i];
             }
         }
         qmco_evolve_state(p, prev->confs, prev->energy,
@@ -823,29 +847,25 @@ QMCO_API void qmco_vmc_block(const double *p, uint64_t seed,
                         ? uniforms_ext + ((st - (first ? 1 : 0)) * num_chains
                                           + c) * (nop + 1)
                         : NULL;
-                    for (int q = 0; 2 * q < nop; ++q) {
-                        double u0, u1;
+                    for (int q = 0; 4 * q < nop; ++q) {
+                        double u4[4] = {0., 0., 0., 0.};
                         if (ue) {
-                            u0 = ue[2 * q];
-                            u1 = (2 * q + 1 < nop) ? ue[2 * q + 1] : 0.;
+                            for (int i = 0; i < 4 && 4 * q + i < nop; ++i)
+                                u4[i] = ue[4 * q + i];
                         } else if (proposal == 1) {
-                            rng_normal2(seed, (uint32_t) (chain_offset + c),
-                                        (uint32_t) q, (uint32_t) g, 2u,
-                                        &u0, &u1);
+                            rng_normal4(seed, (uint32_t) (chain_offset + c),
+                                        (uint32_t) q, (uint32_t) g, 2u, u4);
                         } else {
-                            rng_uniform2(seed, (uint32_t) (chain_offset + c),
-                                         (uint32_t) q, (uint32_t) g, 2u,
-                                         &u0, &u1);
+                            rng_uniform4(seed, (uint32_t) (chain_offset + c),
+                                         (uint32_t) q, (uint32_t) g, 2u, u4);
                         }
-                        double d0 = proposal == 1 ? move_spread * u0
-                                                  : (u0 - 0.5) * move_spread;
-                        double d1 = proposal == 1 ? move_spread * u1
-                                                  : (u1 - 0.5) * move_spread;
-                        prop[2 * q] = recast_to_supercell(cc[2 * q] + d0,
-                                                          z_min, z_max);
-                        if (2 * q + 1 < nop)
-                            prop[2 * q + 1] = recast_to_supercell(
-                                cc[2 * q + 1] + d1, z_min, z_max);
+                        for (int i = 0; i < 4 && 4 * q + i < nop; ++i) {
+                            double d = proposal == 1
+                                ? move_spread * u4[i]
+                                : (u4[i] - 0.5) * move_spread;
+                            prop[4 * q + i] = recast_to_supercell(
+                                cc[4 * q + i] + d, z_min, z_max);
+                        }
                     }
                     double ln_next = wf_abs_log(prop, p);
                     double ua, ub;

@@ -34,6 +34,8 @@ def _find_reference():
     files, git-ignored, travels to the GPU box)."""
     cands = [os.environ.get('QMCB_REFERENCE_SRC'), '/root/reference/src',
              os.path.join(_ROOT, 'baseline', '_ref')]
+    if os.environ.get('QMCB_REFERENCE_ONLY_ENV'):      # tests of the fallback
+        cands = cands[:1]
     for c in cands:
         if c and os.path.isdir(os.path.join(c, 'phd_qmclib')):
             return c

@@ -91,6 +91,9 @@ struct qmcb_handle {
     int max_smem = 0;
     std::string err;
 
+    // node tables of the per-particle transcendentals (TrigTab, device)
+    double4 *d_trig_z = nullptr, *d_trig_c = nullptr;
+
     // scratch for host-pointer model evaluation
     double *d_scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -192,6 +195,7 @@ namespace {
 bool build_model(const qmcb_model_params &p, DevModel &M, std::string &err)
 {
     const double *m = p.model, *o = p.obf, *t = p.tbf;
+    M.tt = TrigTab{};       // tables belong to the handle's own parameters
     double nopd = m[3];
     if (!(nopd >= 1) || nopd != std::floor(nopd) || nopd > 4096) {
         err = "boson_number must be an integer in [1, 4096]";
@@ -244,6 +248,69 @@ bool build_model(const qmcb_model_params &p, DevModel &M, std::string &err)
     M.cpsi[0] = std::cos(psi0); M.spsi[0] = std::sin(psi0);
     M.cpsi[1] = std::cos(psi1); M.spsi[1] = std::sin(psi1);
     return true;
+}
+
+// Node tables for the fast per-particle path (TrigTab in qmcb_dev.cuh).  The
+// node counts keep every residual angle below TRIG_EPS_MAX; a model that
+// would need more than 2^16 nodes keeps the exact sincospi / exp path
+// (M.tt.zt == nullptr).  Entries are rounded from long double.
+int build_trig_tables(qmcb_handle *h)
+{
+    DevModel &M = h->M;
+    M.tt = TrigTab{};
+    cudaFree(h->d_trig_z); cudaFree(h->d_trig_c);
+    h->d_trig_z = h->d_trig_c = nullptr;
+    if (getenv("QMCB_NO_TRIG_TABLES")) return QMCB_OK;
+    auto pow2_at_least = [](double x) {
+        int n = 256;
+        while (n < x && n < (1 << 17)) n <<= 1;
+        return n;
+    };
+    const double per_eps = 0.5 / TRIG_EPS_MAX;      // nodes per radian
+    const double k2 = M.is_ideal ? 0.0 : M.k2;
+    const double k1 = M.is_free ? 0.0 : M.k1, kp1 = M.is_free ? 0.0 : M.kp1;
+    const int nz = pow2_at_least(per_eps * std::max(M_PI, k2 * M.L));
+    const int nc = pow2_at_least(per_eps * std::max(k1, kp1));
+    // sinh/cosh of the barrier argument must stay finite
+    if (nz > (1 << 16) || nc > (1 << 16) || kp1 * 1.0 > 600.0)
+        return QMCB_OK;
+    const long double pi = 3.14159265358979323846264338327950288L;
+    std::vector<double4> zt(nz + 1), ct(nc + 1);
+    for (int k = 0; k <= nz; ++k) {
+        long double a = pi * k / nz;
+        long double u = (long double) k2 * ((long double) M.L * k / nz);
+        zt[k] = make_double4((double) sinl(a), (double) cosl(a),
+                             (double) sinl(u), (double) cosl(u));
+    }
+    zt[nz].x = 0.0;     // sin(pi) exactly
+    for (int j = 0; j <= nc; ++j) {
+        long double zc = (long double) j / nc;
+        long double w = (long double) k1 * (zc - 0.5L * M.za);
+        long double y = (long double) kp1 * (zc - 1.0L + 0.5L * M.zb);
+        ct[j] = make_double4((double) sinl(w), (double) cosl(w),
+                             (double) sinhl(y), (double) coshl(y));
+    }
+    CUDA_TRY(h, cudaMalloc(&h->d_trig_z, zt.size() * sizeof(double4)));
+    CUDA_TRY(h, cudaMalloc(&h->d_trig_c, ct.size() * sizeof(double4)));
+    CUDA_TRY(h, cudaMemcpy(h->d_trig_z, zt.data(),
+                           zt.size() * sizeof(double4),
+                           cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_trig_c, ct.data(),
+                           ct.size() * sizeof(double4),
+                           cudaMemcpyHostToDevice));
+    TrigTab &t = M.tt;
+    t.zt = h->d_trig_z; t.ct = h->d_trig_c;
+    t.nz = nz; t.nc = nc;
+    t.z_scale = nz / M.L; t.eps_a = M_PI / nz; t.eps_u = k2 * M.L / nz;
+    t.c_scale = nc; t.eps_w = k1 / nc; t.eps_b = kp1 / nc;
+    return QMCB_OK;
+}
+
+// The step kernel may take the table path when the sampling recasts into
+// exactly the supercell [0, L] the tables cover.
+bool step_fast_ok(const qmcb_handle *h)
+{
+    return h->M.tt.zt != nullptr && h->C.z_min == 0.0 && h->C.size == h->M.L;
 }
 
 // CTA shape: threads per walker = nb; pack G walkers into a CTA so that few
@@ -798,7 +865,9 @@ int qmcb_create(const qmcb_model_params *params, int device,
     if ((rc = set_smem(h, model_eval_kernel<true, true>)) != QMCB_OK
         || (rc = set_smem(h, model_eval_kernel<true, false>)) != QMCB_OK
         || (rc = set_smem(h, model_eval_kernel<false, true>)) != QMCB_OK
-        || (rc = set_smem(h, dmc_step_kernel)) != QMCB_OK)
+        || (rc = set_smem(h, dmc_step_kernel<false>)) != QMCB_OK
+        || (rc = set_smem(h, dmc_step_kernel<true>)) != QMCB_OK
+        || (rc = build_trig_tables(h)) != QMCB_OK)
         return fail(rc);
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
@@ -814,6 +883,7 @@ void qmcb_destroy(qmcb_handle *h)
     free_dmc(h);
     free_vmc(h);
     cudaFree(h->d_scratch);
+    cudaFree(h->d_trig_z); cudaFree(h->d_trig_c);
     cudaFree(h->d_counts);
     cudaFree(h->rb.sum); cudaFree(h->rb.sqr); cudaFree(h->rb.nblk);
     cudaFree(h->cs_confs); cudaFree(h->cs_ln0); cudaFree(h->cs_work);
@@ -1030,10 +1100,12 @@ int qmcb_set_model_params(qmcb_handle *h, const qmcb_model_params *params)
     CUDA_TRY(h, cudaSetDevice(h->device));
     // kernels in flight hold their own copy of the constants (passed by
     // value), so no synchronisation is needed
+    // the node tables are rebuilt in place: wait for their readers
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->params = *params;
     h->M = M;
     drop_block_graph(h);    // the step kernel's constants are node arguments
-    return QMCB_OK;
+    return build_trig_tables(h);
 }
 
 int qmcb_cs_load(qmcb_handle *h, const double *confs, int64_t nconf,
@@ -1293,6 +1365,7 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
     static const bool no_graph = getenv("QMCB_NO_GRAPH") != nullptr;
     const bool use_graph = !no_graph && !h->comm && !h->profile_steps
                            && !do_ssf && !do_den;
+    const bool step_fast = step_fast_ok(h);
     auto enqueue_step = [&](int64_t i) -> int {
         branch_count_kernel<<<B.nblk, BR_THREADS, 0, h->stream>>>(B, h->C);
         branch_fill_kernel<<<B.nblk, BR_THREADS, 0, h->stream>>>(
@@ -1316,8 +1389,12 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
         }
         if (h->profile_steps)
             CUDA_TRY(h, cudaEventRecord(h->step_ev[2 * i], h->stream));
-        dmc_step_kernel<<<step_grid, g.nthreads, g.smem_bytes, h->stream>>>(
-            h->M, g, B, h->C);
+        if (step_fast)
+            dmc_step_kernel<true><<<step_grid, g.nthreads, g.smem_bytes,
+                                    h->stream>>>(h->M, g, B, h->C);
+        else
+            dmc_step_kernel<false><<<step_grid, g.nthreads, g.smem_bytes,
+                                     h->stream>>>(h->M, g, B, h->C);
         if (h->profile_steps)
             CUDA_TRY(h, cudaEventRecord(h->step_ev[2 * i + 1], h->stream));
         if (h->comm)

@@ -37,6 +37,29 @@ namespace qmcb {
 constexpr int TB = 4;                 // particles owned by one thread
 constexpr double LN2 = 0.693147180559945309417232121458;
 
+// Node tables of the per-particle transcendentals (built once per model on
+// the host, read through L1).  Every sin/cos/sinh/cosh a particle needs is a
+// table entry at the nearest node rotated by the small remaining angle
+// (|eps| <= EPS_MAX, short Taylor polynomials): ~12 fp64 instructions per
+// angle instead of a ~100-instruction sincospi / exp.  Pure functions of z,
+// so nothing is carried between time steps.
+struct TrigTab {
+    const double4 *zt;  // [nz + 1] node z_k = k L / nz:
+                        //   (sin, cos)(pi z_k / L), (sin, cos)(k2 z_k)
+    const double4 *ct;  // [nc + 1] node zc_j = j / nc of the unit cell:
+                        //   (sin, cos)(k1 (zc_j - za/2)),
+                        //   (sinh, cosh)(kp1 (zc_j - 1 + zb/2))
+    double z_scale, eps_a, eps_u;       // nz / L, pi / nz, k2 L / nz
+    double c_scale, eps_w, eps_b;       // nc, k1 / nc, kp1 / nc
+    int nz, nc;
+    // 32-bit word -> node index on the circle of 2 nz nodes
+    __host__ __device__ double z_scale_circle() const
+    {
+        return 2.0 * nz / 4294967296.0;
+    }
+};
+constexpr double TRIG_EPS_MAX = 0.0125;
+
 struct DevModel {
     int nop;            // N
     int nb;             // ceil(N / 4): particle blocks == threads per walker
@@ -58,6 +81,7 @@ struct DevModel {
     double drift_unit;                // -k2       (1 if is_ideal)
     double kin_unit;                  // k2^2      (1 if is_ideal)
     double inv_drift_unit, half_inv_kin_unit;
+    TrigTab tt;                       // zt == nullptr: no tables (exact path)
 };
 
 // Launch geometry shared by every walker-group kernel.
@@ -133,19 +157,23 @@ __device__ __forceinline__ void renorm(double &p, int &e)
 }
 
 // z_min + ((z - z_min) floor-mod (z_max - z_min)); qmc_base/utils.py:55-66.
+// A move leaves the interval by less than its length in all but pathological
+// cases: those take two selects; anything else (and NaN) goes through the
+// out-of-line fmod.
+__device__ __noinline__ double recast_far(double x, double size)
+{
+    double r = fmod(x, size);
+    if (r < 0.0) r += size;
+    return r;
+}
+
 __device__ __forceinline__ double recast(double z, double z_min, double size)
 {
-    double x = z - z_min;
-    if (x >= 0.0 && x < size) return z_min + x;
-    double r;
-    if (x < 0.0 && x >= -size) {
-        r = x + size;                       // Python: fmod(x) = x, then += b
-    } else if (x >= size && x < 2.0 * size) {
-        r = x - size;                       // exact
-    } else {
-        r = fmod(x, size);
-        if (r < 0.0) r += size;
-    }
+    const double x = z - z_min;
+    double r = x;                           // x in [0, size): exact
+    r = (x < 0.0) ? x + size : r;           // Python: fmod(x) = x, then += b
+    r = (x >= size) ? x - size : r;         // exact
+    if (!(x >= -size && x < 2.0 * size)) r = recast_far(x, size);
     return z_min + r;
 }
 
@@ -189,18 +217,113 @@ __device__ __forceinline__ void rng_uniform2(uint64_t seed, uint32_t c0,
     u1 = u53(c[2], c[3]);
 }
 
-__device__ __forceinline__ void rng_normal2(uint64_t seed, uint32_t c0,
-                                            uint32_t c1, uint32_t c2,
-                                            uint32_t stream, double &n0,
-                                            double &n1)
+// Four 32-bit draws of one Philox call.  Convention (shared with the oracle):
+//   uniform  u = (x + 1/2) 2^-32                               in (0, 1)
+//   normals  (Box-Muller) r_a = sqrt(-2 ln((x0 + 1/2) 2^-32)),
+//            (n0, n1) = r_a (cos, sin)(2 pi x1 2^-32); (n2, n3) from x2, x3.
+__device__ __forceinline__ void rng_words4(uint64_t seed, uint32_t c0,
+                                           uint32_t c1, uint32_t c2,
+                                           uint32_t stream, uint32_t (&x)[4])
 {
-    double u0, u1;
-    rng_uniform2(seed, c0, c1, c2, stream, u0, u1);
-    double r = sqrt(-2.0 * log(u0 + 1.0 / 9007199254740992.0));
-    double s, c;
-    sincospi(2.0 * u1, &s, &c);
-    n0 = r * c;
-    n1 = r * s;
+    x[0] = c0; x[1] = c1; x[2] = c2; x[3] = stream;
+    philox4x32_10(x, (uint32_t) seed, (uint32_t) (seed >> 32));
+}
+
+__device__ __forceinline__ double u32_open(uint32_t x)
+{
+    return ((double) x + 0.5) * (1.0 / 4294967296.0);
+}
+
+__device__ __forceinline__ void rng_uniform4(uint64_t seed, uint32_t c0,
+                                             uint32_t c1, uint32_t c2,
+                                             uint32_t stream, double (&u)[4])
+{
+    uint32_t x[4];
+    rng_words4(seed, c0, c1, c2, stream, x);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = u32_open(x[i]);
+}
+
+// one 32-byte table entry through the read-only path (two LDG.128)
+__device__ __forceinline__ double4 ldg4(const double4 *p)
+{
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 a = __ldg(q), b = __ldg(q + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+// sin(e) and cos(e) - 1 for |e| <= TRIG_EPS_MAX (truncation < 1e-17)
+__device__ __forceinline__ void small_sincos(double e, double &se, double &dc)
+{
+    const double s2 = e * e;
+    const double p = fma(s2, 1.0 / 120.0, -1.0 / 6.0);
+    se = fma(e * s2, p, e);
+    double q = fma(s2, -1.0 / 720.0, 1.0 / 24.0);
+    q = fma(s2, q, -0.5);
+    dc = s2 * q;
+}
+
+// sinh(e) and cosh(e) - 1, same range
+__device__ __forceinline__ void small_sinhcosh(double e, double &se,
+                                               double &dc)
+{
+    const double s2 = e * e;
+    const double p = fma(s2, 1.0 / 120.0, 1.0 / 6.0);
+    se = fma(e * s2, p, e);
+    double q = fma(s2, 1.0 / 720.0, 1.0 / 24.0);
+    q = fma(s2, q, 0.5);
+    dc = s2 * q;
+}
+
+// (sin, cos)(t0 + e) from (s0, c0) = (sin, cos)(t0)
+__device__ __forceinline__ void rotate_by(double s0, double c0, double se,
+                                          double dc, double &s, double &c)
+{
+    s = fma(c0, se, fma(s0, dc, s0));
+    c = fma(-s0, se, fma(c0, dc, c0));
+}
+
+// nearest integer of x (|x| < 2^31) and x minus it, without F2I / I2F
+__device__ __forceinline__ int nearest_node(double x, double &frac)
+{
+    const double magic = 6755399441055744.0;        // 1.5 * 2^52
+    const double m = x + magic;
+    frac = x - (m - magic);
+    return __double2loint(m);
+}
+
+template <bool FAST>
+__device__ __forceinline__ void rng_normal4(const TrigTab &tt, uint64_t seed,
+                                            uint32_t c0, uint32_t c1,
+                                            uint32_t c2, uint32_t stream,
+                                            double (&n)[4])
+{
+    uint32_t x[4];
+    rng_words4(seed, c0, c1, c2, stream, x);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const double r = sqrt(-2.0 * log(u32_open(x[2 * h])));
+        double s, c;
+        if (FAST) {
+            // angle 2 pi v = pi (2 v): node k' of 2 nz nodes on the circle;
+            // the table holds the upper half, the lower half is its negative
+            double fr;
+            int k = nearest_node((double) x[2 * h + 1]
+                                 * (tt.z_scale_circle()), fr);
+            const bool lower = k >= tt.nz;
+            k -= lower ? tt.nz : 0;     // k' = 2 nz -> -(sin, cos)(pi) = (0, 1)
+            const double4 e = ldg4(tt.zt + k);
+            double se, dc;
+            small_sincos(fr * tt.eps_a, se, dc);
+            rotate_by(e.x, e.y, se, dc, s, c);
+            s = lower ? -s : s;
+            c = lower ? -c : c;
+        } else {
+            sincospi((double) x[2 * h + 1] * (2.0 / 4294967296.0), &s, &c);
+        }
+        n[2 * h] = r * c;
+        n[2 * h + 1] = r * s;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -238,7 +361,7 @@ __device__ __forceinline__ OneBody one_body(const DevModel &M, double z)
         // mrbp_qmc/model.py:533-551: every defects_sep-th cell is a defect
         double vb = M.vdef;
         if (M.defects_sep != 1
-            && fmod(n_cell, (double) M.defects_sep) != 0.0)
+            && ((int) n_cell % M.defects_sep) != 0)
             vb = M.v0;
         o.pot = barrier ? vb : 0.0;
         o.lnf = 0.0;
@@ -251,7 +374,7 @@ __device__ __forceinline__ OneBody one_body(const DevModel &M, double z)
         o.ldz = M.kp1 * th;
         o.kin = -(M.v0 - M.e0) + o.ldz * o.ldz;
         bool defect = (M.defects_sep == 1)
-                      || (fmod(n_cell, (double) M.defects_sep) == 0.0);
+                      || (((int) n_cell % M.defects_sep) == 0);
         o.pot = defect ? M.vdef : M.v0;
         o.lnf = log(cosh(arg));
     } else {                                        // well
@@ -263,6 +386,58 @@ __device__ __forceinline__ OneBody one_body(const DevModel &M, double z)
         o.lnf = M.ln_cf + log(fabs(c));
     }
     return o;
+}
+
+// Table form of one_body<false> (no ln f1): the well angle and the barrier
+// argument are both continued over the whole unit cell, so one node entry
+// serves either region and the region is a select, not a branch.
+__device__ __forceinline__ OneBody one_body_fast(const DevModel &M, double z)
+{
+    const TrigTab &tt = M.tt;
+    OneBody o;
+    const double n_cell = floor(z);
+    const double zc = z - n_cell;                   // z mod 1, exact
+    const bool barrier = M.za < zc;
+    double fr;
+    int j = nearest_node(zc * tt.c_scale, fr);
+    j = min(max(j, 0), tt.nc);
+    const double4 e = ldg4(tt.ct + j);
+    double se, dc, sw, cw;
+    small_sincos(fr * tt.eps_w, se, dc);
+    rotate_by(e.x, e.y, se, dc, sw, cw);
+    small_sinhcosh(fr * tt.eps_b, se, dc);
+    const double sh = fma(e.w, se, fma(e.z, dc, e.z));
+    const double ch = fma(e.z, se, fma(e.w, dc, e.w));
+    // f1'/f1 = kp1 tanh(.) (barrier) | -k1 tan(.) (well): one reciprocal
+    const double num = barrier ? M.kp1 * sh : -M.k1 * sw;
+    const double den = barrier ? ch : cw;
+    o.ldz = num * fast_rcp(den);
+    // mrbp_qmc/model.py:533-551: every defects_sep-th cell is a defect
+    double vb = M.vdef;
+    if (M.defects_sep != 1 && ((int) n_cell % M.defects_sep) != 0)
+        vb = M.v0;
+    o.kin = fma(o.ldz, o.ldz, barrier ? -(M.v0 - M.e0) : M.e0);
+    o.pot = barrier ? vb : 0.0;
+    o.lnf = 0.0;
+    return o;
+}
+
+// sin/cos tables of one particle from the node table (z in [0, L])
+__device__ __forceinline__ void particle_tables_fast(const DevModel &M,
+                                                     double z, double &sa,
+                                                     double &ca, double &su,
+                                                     double &cu)
+{
+    const TrigTab &tt = M.tt;
+    double fr;
+    int k = nearest_node(z * tt.z_scale, fr);
+    k = min(max(k, 0), tt.nz);
+    const double4 e = ldg4(tt.zt + k);
+    double se, dc;
+    small_sincos(fr * tt.eps_a, se, dc);
+    rotate_by(e.x, e.y, se, dc, sa, ca);
+    small_sincos(fr * tt.eps_u, se, dc);
+    rotate_by(e.z, e.w, se, dc, su, cu);
 }
 
 // sin/cos tables of one particle
@@ -548,7 +723,7 @@ __device__ __forceinline__ void pair_ragged(
 // BCAST: E_L and ln|Psi| of the walker are needed on every one of its threads
 // (the Metropolis test of the VMC kernel); otherwise only thread I == 0 adds
 // up the per-thread partials.
-template <bool LN, bool EF, bool BCAST = true>
+template <bool LN, bool EF, bool BCAST = true, bool FAST = false>
 __device__ __forceinline__ void group_eval(const DevModel &M,
                                            const GroupSmem &sm, int g, int I,
                                            bool active, const double (&z)[TB],
@@ -572,10 +747,17 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
 #pragma unroll
         for (int c = 0; c < TB; ++c) {
             if (c < nvalid) {
-                if (!M.is_ideal)
-                    particle_tables(M, z[c], rsa[c], rca[c], rsu[c], rcu[c]);
+                if (!M.is_ideal) {
+                    if (FAST)
+                        particle_tables_fast(M, z[c], rsa[c], rca[c], rsu[c],
+                                             rcu[c]);
+                    else
+                        particle_tables(M, z[c], rsa[c], rca[c], rsu[c],
+                                        rcu[c]);
+                }
                 if (!M.is_free) {
-                    OneBody ob = one_body<LN>(M, z[c]);
+                    OneBody ob = (FAST && !LN) ? one_body_fast(M, z[c])
+                                               : one_body<LN>(M, z[c]);
                     acc.T[c] = ob.ldz * M.inv_drift_unit;
                     e1 += ob.kin + ob.pot;
                     if (LN) ln1 += ob.lnf;

@@ -477,6 +477,10 @@ __global__ void dmc_finalize_kernel(DmcBufs B, DmcConsts C, DmcLog L)
 #ifndef QMCB_STEP_MINCTAS
 #define QMCB_STEP_MINCTAS 2
 #endif
+// FAST: the per-particle transcendentals come from the model's node tables
+// (TrigTab); needs positions in [0, L], i.e. the recast interval of the
+// sampling equal to the supercell (checked by the host).
+template <bool FAST>
 __global__ void __launch_bounds__(QMCB_STEP_THREADS, QMCB_STEP_MINCTAS)
 dmc_step_kernel(const __grid_constant__ DevModel M, GroupGeom geom, DmcBufs B,
                 DmcConsts C)
@@ -513,10 +517,8 @@ dmc_step_kernel(const __grid_constant__ DevModel M, GroupGeom geom, DmcBufs B,
         load4(pc + N, x.I, nvalid, vec_ok, fp);
         double nrm[TB];
         const uint32_t gs = (uint32_t) (C.slot_offset + s);
-        rng_normal2(C.seed, gs, (uint32_t) (2 * x.I), (uint32_t) t,
-                    STREAM_DIFFUSE, nrm[0], nrm[1]);
-        rng_normal2(C.seed, gs, (uint32_t) (2 * x.I + 1), (uint32_t) t,
-                    STREAM_DIFFUSE, nrm[2], nrm[3]);
+        rng_normal4<FAST>(M.tt, C.seed, gs, (uint32_t) x.I, (uint32_t) t,
+                          STREAM_DIFFUSE, nrm);
 #pragma unroll
         for (int c = 0; c < TB; ++c) {
             double zn = zp[c] + 2.0 * fp[c] * C.dt + C.sigma * nrm[c];
@@ -526,7 +528,8 @@ dmc_step_kernel(const __grid_constant__ DevModel M, GroupGeom geom, DmcBufs B,
         store4(nconfs + s * 2 * N, x.I, nvalid, vec_ok, z);
     }
     EvalOut o;
-    group_eval<false, true, false>(M, sm, x.g, x.I, active, z, nvalid, o);
+    group_eval<false, true, false, FAST>(M, sm, x.g, x.I, active, z, nvalid,
+                                         o);
     if (active) {
         double *nc = nconfs + s * 2 * N;
         store4(nc + N, x.I, nvalid, vec_ok, o.F);

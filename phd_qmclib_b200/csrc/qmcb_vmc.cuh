@@ -74,19 +74,15 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
             if (active && !ini) {
                 double u[TB];
                 if (a.proposal == 1) {
-                    rng_normal2(a.seed, gc, (uint32_t) (2 * x.I),
-                                (uint32_t) gs, STREAM_VMC_MOVE, u[0], u[1]);
-                    rng_normal2(a.seed, gc, (uint32_t) (2 * x.I + 1),
-                                (uint32_t) gs, STREAM_VMC_MOVE, u[2], u[3]);
+                    rng_normal4<false>(M.tt, a.seed, gc, (uint32_t) x.I,
+                                       (uint32_t) gs, STREAM_VMC_MOVE, u);
 #pragma unroll
                     for (int q = 0; q < TB; ++q)
                         zp[q] = recast(z[q] + a.spread * u[q], a.z_min,
                                        a.size);
                 } else {
-                    rng_uniform2(a.seed, gc, (uint32_t) (2 * x.I),
-                                 (uint32_t) gs, STREAM_VMC_MOVE, u[0], u[1]);
-                    rng_uniform2(a.seed, gc, (uint32_t) (2 * x.I + 1),
-                                 (uint32_t) gs, STREAM_VMC_MOVE, u[2], u[3]);
+                    rng_uniform4(a.seed, gc, (uint32_t) x.I, (uint32_t) gs,
+                                 STREAM_VMC_MOVE, u);
 #pragma unroll
                     for (int q = 0; q < TB; ++q)
                         zp[q] = recast(z[q] + (u[q] - 0.5) * a.spread,
