@@ -221,18 +221,21 @@ def workload_config(name, cfg, args, world):
         'time_steps_per_step': args.nts,
         'estimators': est,
         'parallelism': f'walkers sharded over {world} GPU(s)',
-        'l2_policy': ('working set (2 x %.0f MB walker buffers%s) %s the '
-                      '126 MB L2' % (
-                          args.walkers * CAP_FACTOR * 16 * n / 1e6,
-                          ' + %.0f MB S(k) rows' % (
-                              2 * args.walkers * CAP_FACTOR * 24
-                              * cfg['modes'] / 1e6) if cfg['modes'] else '',
-                          'exceeds' if args.walkers * CAP_FACTOR * 32 * n
-                          + 2 * args.walkers * CAP_FACTOR * 24 * cfg['modes']
-                          > 126e6 else 'fits (the configuration BASELINE '
-                          'names is this small); L2 flushed between timed '
-                          'blocks by a 256 MB memset: see l2_flush')),
+        'l2_policy': _l2_policy(cfg, args),
     }
+
+
+def _l2_policy(cfg, args):
+    n, M = cfg['nop'], cfg['modes']
+    cap = args.walkers * CAP_FACTOR
+    txt = 'working set (2 x %.0f MB walker buffers' % (cap * 16 * n / 1e6)
+    if M:
+        txt += ' + %.0f MB S(k) rows' % (2 * cap * 24 * M / 1e6)
+    if cap * 32 * n + 2 * cap * 24 * M > 126e6:
+        return txt + ') exceeds the 126 MB L2'
+    return txt + (') fits the 126 MB L2 (the configuration BASELINE names is '
+                  'this small): L2 flushed before every timed block by a '
+                  '256 MB memset outside the timed events')
 
 
 # ---------------------------------------------------------------------------
@@ -533,7 +536,12 @@ def run_dmc(name, cfg, args, D):
                           ssf=ssf)
 
     # ---- device-resident timing ------------------------------------------
-    eng.set_profiling(True)
+    # Per-launch events (set_profiling) give the step kernel's time inside
+    # the timed region, but rule out the CUDA graph a launch-bound block
+    # replays; small populations are therefore timed as the product runs
+    # them and the kernel time comes from extra profiled blocks afterwards.
+    profile_in_region = world > 1 or est or cap * n >= 2000000
+    eng.set_profiling(profile_in_region)
     moved = 0
     for _ in range(args.warmup):
         block()
@@ -545,7 +553,7 @@ def run_dmc(name, cfg, args, D):
         time.sleep(0.3)
     D.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
-    ws_total, kern_ms, launches, dev_ms = 0.0, 0.0, 0, 0.0
+    ws_total, kern_ms, launches, dev_ms, kern_ws = 0.0, 0.0, 0, 0.0, 0.0
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     if flush is None:
@@ -559,6 +567,7 @@ def run_dmc(name, cfg, args, D):
         st = eng.last_block_stats()
         kern_ms += st['step_kernel_ms']
         launches += st['launches']
+        kern_ws += float(series['num_walkers'].sum())
         ws_total += float(series['num_walkers'].sum())   # GLOBAL if world > 1
         if world > 1:
             # order-preserving neighbour shifts, once per block, timed
@@ -582,24 +591,39 @@ def run_dmc(name, cfg, args, D):
     n_local = float(eng.dmc_scalars().num_walkers)
     per_rank = {'walkers': D.gather(n_local),
                 'step_kernel_ms_per_launch': D.gather(
-                    kern_ms / (args.steps * nts)),
+                    kern_ms / (args.steps * nts) if profile_in_region
+                    else float('nan')),
                 'block_ms': D.gather(local_ms / args.steps)}
 
+    kern_blocks = args.steps
+    if not profile_in_region:
+        eng.set_profiling(True)
+        kern_ms, kern_ws, kern_blocks = 0.0, 0.0, 3
+        for _ in range(kern_blocks):
+            block()
+            kern_ms += eng.last_block_stats()['step_kernel_ms']
+            kern_ws += float(series['num_walkers'].sum())
+
     # roofline of the step kernel (this rank's launches, this rank's walkers)
-    ws_rank = ws_total / world
+    ws_rank = kern_ws / world
     F = flops_per_walker_step(n)
     ach_tf = ws_rank * F / (kern_ms * 1e-3) / 1e12
     hbm_gbs = ws_rank * bytes_per_walker_step(n) / (kern_ms * 1e-3) / 1e9
     view = committed_ncu_view(name) or {}
     traffic = None
     if view.get('dram_bytes_per_walker') is not None:
-        traffic = view['dram_bytes_per_walker'] * ws_rank / (args.steps * nts)
+        traffic = view['dram_bytes_per_walker'] * ws_rank / (kern_blocks * nts)
     peaks = measured_peaks()
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     roofline = roofline_fp64('dmc_step_kernel', ach_tf, peak_sust, peak_burst, {
         'flop_per_walker_step': F,
-        'avg_launch_ms': kern_ms / (args.steps * nts),
-        'step_kernel_share_of_step': kern_ms / dev_ms,
+        'avg_launch_ms': kern_ms / (kern_blocks * nts),
+        'step_kernel_share_of_step': (kern_ms / kern_blocks) / ms_per_step,
+        'kernel_timing': ('CUDA events around every launch inside the timed '
+                          'region' if profile_in_region else
+                          f'CUDA events around every launch of {kern_blocks} '
+                          f'extra blocks after the timed region (the timed '
+                          f'blocks replay a CUDA graph)'),
         'traffic': traffic, 'ncu': view or None,
         'hbm': {'achieved': hbm_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                 'frac': hbm_gbs / hbm_peak,
@@ -696,12 +720,12 @@ def run_vmc(name, cfg, args, D):
     D.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     e0.record(stream)
-    kern_ms, acc, esum = 0.0, 0.0, 0.0
+    kern_ms, acc = 0.0, 0.0
     for _ in range(args.steps):
-        o = eng.vmc_run_block(ns, series=False, sums=True)
+        # the per-chain sums stay on the device (accumulated by the kernel)
+        o = eng.vmc_run_block(ns, series=False, sums=False)
         kern_ms += eng.last_block_stats()['total_ms']
         acc += float(o['accept_rate'].mean())
-        esum = float(o['sum_energy'][:, 0].mean() / ns / n)
     e1.record(stream)
     D.barrier(); torch.cuda.synchronize()
     t1 = time.perf_counter()
@@ -719,6 +743,9 @@ def run_vmc(name, cfg, args, D):
         'kernel_share_of_step': kern_ms / dev_ms,
         'traffic': None, 'ncu': committed_ncu_view(name),
     })
+
+    o = eng.vmc_run_block(ns, series=False, sums=True)
+    esum = float(o['sum_energy'][:, 0].mean() / ns / n)
 
     # ---- end to end: chains from host, block, per-chain sums to host ------
     confs, _ = eng.vmc_get_state()

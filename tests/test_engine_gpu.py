@@ -528,15 +528,16 @@ def test_density_bin_edges_vs_oracle(eng_mod, oracle, pure):
     bins, n_ini, wmax, nts = 37, 40, 64, 3
     width = size / bins
     rng = np.random.default_rng(12)
-    k = rng.integers(0, bins, size=(n_ini, nop)).astype(np.float64)
+    # distinct bins within a walker: two particles at exactly the same
+    # position have no defined sign(d) (the reference gives both +f2'/f2, an
+    # antisymmetric pair evaluation gives +-), which is not what this test
+    # is about
+    k = np.argsort(rng.random((n_ini, bins)), axis=1)[:, :nop] \
+        .astype(np.float64)
     z = k * width
     z[1::3] = np.nextafter(z[1::3], np.inf)
     z[2::3] = np.nextafter(z[2::3], -np.inf)
     z = np.clip(z, 0.0, np.nextafter(size, 0.0))
-    # keep the particles of a walker apart (coincident particles are not
-    # what this test is about)
-    z += 1e-3 * width * np.argsort(rng.random((n_ini, nop)), axis=1) \
-        * (rng.random((n_ini, 1)) < 0.5)
     ini = np.zeros((n_ini, 2, nop))
     ini[:, 0] = z
     st = oracle.DMCState(p, ini, wmax)
