@@ -144,6 +144,7 @@ struct qmcb_handle {
 
     // VMC
     bool vmc_ready = false;
+    bool vmc_fast = false;      // block kernel on the node tables
     qmcb_vmc_params vp{};
     VmcState V{};
     long long vmc_chains = 0, vmc_gstep = 0;
@@ -1974,7 +1975,10 @@ int qmcb_vmc_init(qmcb_handle *h, const qmcb_vmc_params *params,
     if (vsm > (size_t) h->max_smem)
         FAIL(h, QMCB_ERR_INVALID, "boson_number too large for the VMC kernel");
     CUDA_TRY(h, cudaFuncSetAttribute(
-                    vmc_block_kernel,
+                    vmc_block_kernel<false>,
+                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int) vsm));
+    CUDA_TRY(h, cudaFuncSetAttribute(
+                    vmc_block_kernel<true>,
                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) vsm));
     free_vmc(h);
     h->vp = *params;
@@ -2002,6 +2006,20 @@ int qmcb_vmc_init(qmcb_handle *h, const qmcb_vmc_params *params,
     int rc = launch_model_eval(h, a, true, false);
     if (rc) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    // the table path of the block kernel needs every position in [0, L]
+    h->vmc_fast = h->M.tt.zt != nullptr && params->lower_bound == 0.0
+                  && params->upper_bound - params->lower_bound == h->M.L;
+    if (h->vmc_fast) {
+        const size_t row = (size_t) N;
+        for (size_t c = 0; c < C && h->vmc_fast; ++c) {
+            const double *zr = confs + c * 2 * row;
+            for (size_t i = 0; i < row; ++i)
+                if (!(zr[i] >= 0.0 && zr[i] <= h->M.L)) {
+                    h->vmc_fast = false;
+                    break;
+                }
+        }
+    }
     h->vmc_chains = num_chains;
     h->vmc_gstep = 0;
     h->vmc_first = 1;
@@ -2055,7 +2073,12 @@ int qmcb_vmc_run_block(qmcb_handle *h, int64_t ns, double *lnpsi,
     long long ctas = ((long long) C + g.G - 1) / g.G;
     int grid = (int) std::min<long long>(ctas, (long long) h->sm_count * 64);
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
-    vmc_block_kernel<<<grid, g.nthreads, vsm, h->stream>>>(h->M, g, h->V, a);
+    if (h->vmc_fast)
+        vmc_block_kernel<true><<<grid, g.nthreads, vsm, h->stream>>>(
+            h->M, g, h->V, a);
+    else
+        vmc_block_kernel<false><<<grid, g.nthreads, vsm, h->stream>>>(
+            h->M, g, h->V, a);
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     h->vmc_gstep += ns - (h->vmc_first ? 1 : 0);

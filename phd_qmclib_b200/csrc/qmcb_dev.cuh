@@ -422,6 +422,42 @@ __device__ __forceinline__ OneBody one_body_fast(const DevModel &M, double z)
     return o;
 }
 
+// Table form of one_body<true>: |f1| comes back as a factor (cosh in the
+// barrier, cos in the well, where ln cf is added per well particle by the
+// caller) so that a thread takes ONE logarithm for its four particles.
+__device__ __forceinline__ OneBody one_body_fast_ln(const DevModel &M,
+                                                    double z, double &f1abs,
+                                                    int &in_well)
+{
+    const TrigTab &tt = M.tt;
+    OneBody o;
+    const double n_cell = floor(z);
+    const double zc = z - n_cell;
+    const bool barrier = M.za < zc;
+    double fr;
+    int j = nearest_node(zc * tt.c_scale, fr);
+    j = min(max(j, 0), tt.nc);
+    const double4 e = ldg4(tt.ct + j);
+    double se, dc, sw, cw;
+    small_sincos(fr * tt.eps_w, se, dc);
+    rotate_by(e.x, e.y, se, dc, sw, cw);
+    small_sinhcosh(fr * tt.eps_b, se, dc);
+    const double sh = fma(e.w, se, fma(e.z, dc, e.z));
+    const double ch = fma(e.z, se, fma(e.w, dc, e.w));
+    const double num = barrier ? M.kp1 * sh : -M.k1 * sw;
+    const double den = barrier ? ch : cw;
+    o.ldz = num * fast_rcp(den);
+    double vb = M.vdef;
+    if (M.defects_sep != 1 && ((int) n_cell % M.defects_sep) != 0)
+        vb = M.v0;
+    o.kin = fma(o.ldz, o.ldz, barrier ? -(M.v0 - M.e0) : M.e0);
+    o.pot = barrier ? vb : 0.0;
+    o.lnf = 0.0;
+    f1abs = fabs(den);
+    in_well = barrier ? 0 : 1;
+    return o;
+}
+
 // sin/cos tables of one particle from the node table (z in [0, L])
 __device__ __forceinline__ void particle_tables_fast(const DevModel &M,
                                                      double z, double &sa,
@@ -743,7 +779,8 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
         rsa[c] = 0.0; rca[c] = 1.0; rsu[c] = 0.0; rcu[c] = 1.0;
     }
     if (active) {
-        double e1 = 0.0;
+        double e1 = 0.0, p1 = 1.0;      // p1: product of |f1| (FAST && LN)
+        int nwell = 0;
 #pragma unroll
         for (int c = 0; c < TB; ++c) {
             if (c < nvalid) {
@@ -756,8 +793,18 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
                                         rcu[c]);
                 }
                 if (!M.is_free) {
-                    OneBody ob = (FAST && !LN) ? one_body_fast(M, z[c])
-                                               : one_body<LN>(M, z[c]);
+                    OneBody ob;
+                    if (FAST && LN) {
+                        double f1;
+                        int w;
+                        ob = one_body_fast_ln(M, z[c], f1, w);
+                        p1 *= f1;
+                        nwell += w;
+                    } else if (FAST) {
+                        ob = one_body_fast(M, z[c]);
+                    } else {
+                        ob = one_body<LN>(M, z[c]);
+                    }
                     acc.T[c] = ob.ldz * M.inv_drift_unit;
                     e1 += ob.kin + ob.pot;
                     if (LN) ln1 += ob.lnf;
@@ -783,6 +830,9 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
             }
         }
         acc.K = e1 * M.half_inv_kin_unit;
+        // four factors of at most cosh(kp1 zb / 2) each: no overflow
+        // (the tables are not built for kp1 > 600)
+        if (FAST && LN && !M.is_free) ln1 = log(p1) + nwell * M.ln_cf;
     }
     __syncthreads();
 

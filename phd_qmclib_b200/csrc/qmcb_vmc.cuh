@@ -39,6 +39,10 @@ struct VmcArgs {
     double *sum_ssf;                    // [C][M][3] or null
 };
 
+// FAST: node-table transcendentals (TrigTab); needs every position in
+// [0, L]: the recast interval equal to the supercell and initial positions
+// inside it (checked by the host).
+template <bool FAST>
 __global__ void __launch_bounds__(256, 2)
 vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                  VmcState S, VmcArgs a)
@@ -74,7 +78,7 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
             if (active && !ini) {
                 double u[TB];
                 if (a.proposal == 1) {
-                    rng_normal4<false>(M.tt, a.seed, gc, (uint32_t) x.I,
+                    rng_normal4<FAST>(M.tt, a.seed, gc, (uint32_t) x.I,
                                        (uint32_t) gs, STREAM_VMC_MOVE, u);
 #pragma unroll
                     for (int q = 0; q < TB; ++q)
@@ -90,7 +94,8 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                 }
             }
             EvalOut o;
-            group_eval<true, true>(M, sm, x.g, x.I, active, zp, nvalid, o);
+            group_eval<true, true, true, FAST>(M, sm, x.g, x.I, active, zp,
+                                               nvalid, o);
             bool take = false;
             if (active) {
                 if (ini) {
