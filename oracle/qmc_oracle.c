@@ -379,8 +379,11 @@ QMCO_API void qmco_one_body_density(const double *p, const double *confs,
 /*   Philox4x32-10, key = (seed_lo, seed_hi).                          */
 /*   counter = (c0, c1, c2, stream):                                   */
 /*     stream 0  DMC branching   c0 = global slot, c1 = 0, c2 = step   */
-/*     stream 1  DMC diffusion   c0 = global slot, c1 = q,  c2 = step  */
-/*               -> normals for particles 4q .. 4q+3                   */
+/*     stream 1  DMC diffusion   c0 = global slot of the PARENT,       */
+/*               c1 = q | (clone index << 16), c2 = step               */
+/*               -> normals for particles 4q .. 4q+3 of the parent's   */
+/*               clone-th child (independent of how a multi-GPU run    */
+/*               cuts the ensemble into ranks)                         */
 /*     stream 2  VMC proposal    c0 = chain, c1 = q, c2 = step         */
 /*               -> uniforms / normals for particles 4q .. 4q+3        */
 /*     stream 3  VMC acceptance  c0 = chain, c1 = 0, c2 = step         */
@@ -737,6 +740,10 @@ QMCO_API void qmco_dmc_block(const double *p, uint64_t seed,
                                  unif, cloning_ref);
 #pragma omp parallel for schedule(static)
         for (int64_t s = 0; s < nw; ++s) {
+            int64_t clone = 0;
+            while (clone < 0xffff && s - clone - 1 >= 0
+                   && cloning_ref[s - clone - 1] == cloning_ref[s])
+                ++clone;
             for (int q = 0; 4 * q < nop; ++q) {
                 double n4[4] = {0., 0., 0., 0.};
                 if (normals_ext) {
@@ -745,7 +752,8 @@ QMCO_API void qmco_dmc_block(const double *p, uint64_t seed,
                     for (int i = 0; i < 4 && 4 * q + i < nop; ++i)
                         n4[i] = ne[4 * q + i];
                 } else {
-                    rng_normal4(seed, (uint32_t) s, (uint32_t) q,
+                    rng_normal4(seed, (uint32_t) cloning_ref[s],
+                                (uint32_t) q | ((uint32_t) clone << 16),
                                 (uint32_t) gstep, 1u, n4);
                 }
                 for (int i = 0; i < 4 && 4 * q + i < nop; ++i)

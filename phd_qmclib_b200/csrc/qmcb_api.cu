@@ -158,6 +158,10 @@ struct qmcb_handle {
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
     long long *d_counts = nullptr;      // [world] live walkers per rank
+    DmcMulti X{};                       // global stale-slot array and the
+    bool multi_ready = false;           // per-step collective buffers
+    long long rebalance_every = 32;     // in-block check period (steps)
+    long long rebalanced_in_block = 0;
 };
 
 #define CUDA_TRY(h, expr)                                                    \
@@ -444,6 +448,10 @@ void free_dmc(qmcb_handle *h)
     h->est_log_cap = 0;
     cudaFree(h->L.energy); cudaFree(h->L.weight); cudaFree(h->L.ref_energy);
     cudaFree(h->L.accum_energy); cudaFree(h->L.num_walkers);
+    cudaFree(h->X.aglob); cudaFree(h->X.slab); cudaFree(h->X.gathered);
+    cudaFree(h->X.vred); cudaFree(h->X.offs);
+    h->X = DmcMulti{};
+    h->multi_ready = false;
     B = DmcBufs{};
     h->L = DmcLog{};
     h->log_cap = 0;
@@ -552,13 +560,17 @@ int alloc_dmc(qmcb_handle *h, const qmcb_dmc_params *p,
     C.seed = p->rng_seed;
     C.slot_offset = slot_offset;
     C.energy_mode = p->energy_mode;
+    C.defer_weight = (h->comm && p->energy_mode == 0) ? 1 : 0;
+    h->multi_ready = false;     // the global stale-slot array is rebuilt from
+                                // the state about to be loaded
     // the nodes of the block graph hold the constants by value (a
     // reallocation has already dropped it in free_dmc)
     if (old_c.dt != C.dt || old_c.sigma != C.sigma || old_c.z_min != C.z_min
         || old_c.size != C.size || old_c.nwc_over_dt != C.nwc_over_dt
         || old_c.target != C.target || old_c.seed != C.seed
         || old_c.slot_offset != C.slot_offset
-        || old_c.energy_mode != C.energy_mode)
+        || old_c.energy_mode != C.energy_mode
+        || old_c.defer_weight != C.defer_weight)
         drop_block_graph(h);
     return QMCB_OK;
 }
@@ -801,6 +813,66 @@ void fill_scalars(const qmcb_handle *h, const DmcCtl &ctl,
     s->max_num_walkers = h->B.cap;
     s->step = ctl.step;
     s->capacity_hits = ctl.capacity_hits;
+}
+
+// Sharded runs: allocate the buffers of the per-step collectives and
+// (re)build the replicated global stale-slot array from the local arrays of
+// all ranks.  Import convention (qmcb_dmc_init / qmcb_dmc_set_state): rank q
+// holds, at local index i < n_q, A at the global position o_q + i of its
+// i-th walker; the entries of the LAST rank beyond its population are the
+// tail of the global array (positions beyond the live ensemble).
+int multi_setup(qmcb_handle *h)
+{
+    if (!h->comm || h->multi_ready) return QMCB_OK;
+    NcclApi *api = nccl_api();
+    DmcBufs &B = h->B;
+    DmcMulti &X = h->X;
+    const int R = h->world, me = h->rank;
+    if (!X.aglob || X.cap != B.cap || X.R != R) {
+        cudaFree(X.aglob); cudaFree(X.slab); cudaFree(X.gathered);
+        cudaFree(X.vred); cudaFree(X.offs);
+        X = DmcMulti{};
+        const size_t rc = (size_t) R * B.cap;
+        CUDA_TRY(h, cudaMalloc(&X.aglob, rc * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc(&X.gathered, rc * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc(&X.slab, (size_t) B.cap * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc(&X.vred, (R + 2) * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc(&X.offs, (R + 1) * sizeof(long long)));
+        X.R = R; X.rank = me; X.cap = B.cap;
+    }
+    DmcCtl ctl;
+    int rc = read_ctl(h, ctl);
+    if (rc) return rc;
+    long long mine = ctl.W_prev;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_counts + me, &mine, sizeof mine,
+                                cudaMemcpyHostToDevice, h->stream));
+    NCCL_TRY(h, api->AllGather(h->d_counts + me, h->d_counts, 1, ncclInt64,
+                               h->comm, h->stream));
+    std::vector<long long> cnt(R), offs(R + 1, 0);
+    CUDA_TRY(h, cudaMemcpyAsync(cnt.data(), h->d_counts,
+                                R * sizeof(long long), cudaMemcpyDeviceToHost,
+                                h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int q = 0; q < R; ++q) offs[q + 1] = offs[q] + cnt[q];
+    CUDA_TRY(h, cudaMemcpyAsync(X.offs, offs.data(),
+                                (R + 1) * sizeof(long long),
+                                cudaMemcpyHostToDevice, h->stream));
+    long long pb[2] = {offs[me], offs[me]};
+    CUDA_TRY(h, cudaMemcpyAsync(
+                    (char *) B.ctl + offsetof(DmcCtl, pos_base), pb, sizeof pb,
+                    cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(X.aglob, 0,
+                                (size_t) R * B.cap * sizeof(double),
+                                h->stream));
+    NCCL_TRY(h, api->AllGather(B.slot_energy, X.gathered, B.cap, ncclDouble,
+                               h->comm, h->stream));
+    const int grid = h->sm_count * 4;
+    multi_apply_kernel<<<grid, 256, 0, h->stream>>>(X);
+    multi_tail_kernel<<<grid, 256, 0, h->stream>>>(X, cnt[R - 1]);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->multi_ready = true;
+    return QMCB_OK;
 }
 
 }  // namespace
@@ -1247,6 +1319,7 @@ int qmcb_dmc_init(qmcb_handle *h, const qmcb_dmc_params *params,
     ctl.eref[0] = std::isnan(ref_energy) ? ctl.last_accum : ref_energy;
     ctl.eref[1] = ctl.eref[0];
     ctl.W_global = n_glob;
+    ctl.pos_base[0] = ctl.pos_base[1] = global_slot_offset;
     CUDA_TRY(h, cudaMemcpyAsync(B.ctl, &ctl, sizeof ctl,
                                 cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1300,6 +1373,7 @@ int qmcb_dmc_set_state(qmcb_handle *h, const qmcb_dmc_params *params,
     ctl.last_weight = sc->weight;
     ctl.last_accum = sc->accum_energy;
     ctl.W_global = sc->weight;
+    ctl.pos_base[0] = ctl.pos_base[1] = global_slot_offset;
     CUDA_TRY(h, cudaMemcpyAsync(B.ctl, &ctl, sizeof ctl,
                                 cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1352,6 +1426,13 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
     DmcLog L = h->L;
     const GroupGeom &g = h->geom;
     const int step_grid = (B.cap + g.G - 1) / g.G;
+    if (h->comm) {
+        rc = multi_setup(h);
+        if (rc) return rc;
+    }
+    const DmcMulti X = h->X;
+    const bool glob_a = h->comm && h->C.defer_weight;
+    h->rebalanced_in_block = 0;
     if (h->profile_steps) {
         while ((long long) h->step_ev.size() < 2 * nts) {
             cudaEvent_t ev;
@@ -1372,20 +1453,28 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
         branch_fill_kernel<<<B.nblk, BR_THREADS, 0, h->stream>>>(
             B, h->C, L, h->comm ? 0 : 1);
         if (h->comm) {
-            // population control needs the GLOBAL {sum E, W}
-            // (qmc_base/dmc.py:758-771): 16 bytes, all-reduced in place, then
-            // dmc_finalize.  The step kernel of this time step needs neither
-            // (it reads E_ref of the previous step and its own step index
-            // from ctl->tcur), so both run on a second stream next to it; the
-            // next step's branching waits for them.
+            // Population control needs the GLOBAL {sum E, W}
+            // (qmc_base/dmc.py:758-771) and, with the reference's stale-slot
+            // weights, every rank needs the values the others write into
+            // the global per-position array: one all-reduce of R + 2 doubles
+            // (sums and the counts of all ranks) and one all-gather of 8
+            // bytes per slot.  The step kernel of this time step needs none
+            // of it (it reads E_ref of the previous step and its step index
+            // from ctl->tcur), so all of this runs on a second stream next
+            // to it; the weights (multi_weight_kernel) and the next step's
+            // branching wait for it.
             CUDA_TRY(h, cudaEventRecord(h->ev_branched, h->stream));
             CUDA_TRY(h, cudaStreamWaitEvent(h->pc_stream, h->ev_branched, 0));
-            NCCL_TRY(h, nccl_api()->AllReduce(
-                            (const void *) ((char *) B.ctl
-                                            + offsetof(DmcCtl, red)),
-                            (void *) ((char *) B.ctl + offsetof(DmcCtl, red)),
-                            2, ncclDouble, ncclSum, h->comm, h->pc_stream));
-            dmc_finalize_kernel<<<1, 32, 0, h->pc_stream>>>(B, h->C, L);
+            multi_pack_kernel<<<glob_a ? (B.cap + 255) / 256 : 1, 256, 0,
+                                h->pc_stream>>>(B, X, glob_a ? 1 : 0);
+            NCCL_TRY(h, nccl_api()->AllReduce(X.vred, X.vred, X.R + 2,
+                                              ncclDouble, ncclSum, h->comm,
+                                              h->pc_stream));
+            if (glob_a)
+                NCCL_TRY(h, nccl_api()->AllGather(X.slab, X.gathered, B.cap,
+                                                  ncclDouble, h->comm,
+                                                  h->pc_stream));
+            multi_finalize_kernel<<<1, 32, 0, h->pc_stream>>>(B, h->C, L, X);
             CUDA_TRY(h, cudaEventRecord(h->ev_controlled, h->pc_stream));
         }
         if (h->profile_steps)
@@ -1398,8 +1487,14 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
                                      h->stream>>>(h->M, g, B, h->C);
         if (h->profile_steps)
             CUDA_TRY(h, cudaEventRecord(h->step_ev[2 * i + 1], h->stream));
-        if (h->comm)
+        if (h->comm) {
             CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_controlled, 0));
+            if (glob_a) {
+                const int grid = h->sm_count * 4;
+                multi_weight_kernel<<<grid, 256, 0, h->stream>>>(B, h->C, X);
+                multi_apply_kernel<<<grid, 256, 0, h->stream>>>(X);
+            }
+        }
         return QMCB_OK;
     };
     if (use_graph && (!h->block_graph || h->block_graph_nts != nts)) {
@@ -1444,6 +1539,43 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
             if (rc) return rc;
             est_launches += 3;
         }
+        // Sharded runs without per-slot estimator state: every
+        // `rebalance_every` steps look at the counts of all ranks (one
+        // 8 (R + 1)-byte read) and even the slabs out when they have drifted
+        // apart by more than 2 %, or when one of them nears its capacity
+        // (the reference truncates at the GLOBAL capacity only).
+        if (h->comm && !do_ssf && !do_den && h->rebalance_every > 0
+            && (i + 1) % h->rebalance_every == 0 && i + 1 < nts) {
+            std::vector<long long> offs(X.R + 1);
+            CUDA_TRY(h, cudaMemcpyAsync(offs.data(), X.offs,
+                                        (X.R + 1) * sizeof(long long),
+                                        cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            long long mx = 0, mn = 1ll << 62;
+            for (int q = 0; q < X.R; ++q) {
+                mx = std::max(mx, offs[q + 1] - offs[q]);
+                mn = std::min(mn, offs[q + 1] - offs[q]);
+            }
+            if (mx - mn > 1 && ((double) mx > 1.02 * (double) mn
+                                || (double) mx > 0.9 * (double) B.cap)) {
+                int64_t mv = 0;
+                rc = qmcb_dmc_rebalance(h, &mv);
+                if (rc) return rc;
+                h->rebalanced_in_block += mv;
+            }
+        }
+    }
+    if (h->comm && (do_den || do_ssf)) {
+        // the tables hold this rank's partial sums: global sums on the
+        // device, before they leave for the host
+        if (do_den)
+            NCCL_TRY(h, nccl_api()->AllReduce(h->den_iter, h->den_iter,
+                                              nts * (size_t) NB, ncclDouble,
+                                              ncclSum, h->comm, h->stream));
+        if (do_ssf)
+            NCCL_TRY(h, nccl_api()->AllReduce(h->ssf_iter, h->ssf_iter,
+                                              nts * (size_t) M3, ncclDouble,
+                                              ncclSum, h->comm, h->stream));
     }
     if (h->rb.K > 0) {
         // same expression as on_the_fly_obj_data_order (stats/reblock.py:447)
@@ -1454,7 +1586,8 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     h->step_host += nts;
-    h->last_launches = 1 + (3 + (h->comm ? 2 : 0)) * nts + est_launches;
+    h->last_launches = 1 + (3 + (h->comm ? (glob_a ? 4 : 2) : 0)) * nts
+                       + est_launches;
     if (density && do_den)
         CUDA_TRY(h, cudaMemcpyAsync(density, h->den_iter,
                                     nts * (size_t) NB * sizeof(double),
@@ -1640,10 +1773,18 @@ int qmcb_dmc_get_next(qmcb_handle *h, double *confs, double *energy,
     if (weight)
         CUDA_TRY(h, cudaMemcpyAsync(weight, B.weight[par], n * sizeof(double),
                                     cudaMemcpyDeviceToHost, h->stream));
-    if (slot_energy)
+    if (slot_energy) {
+        if (h->comm && h->C.defer_weight && h->multi_ready) {
+            // the local view of the global per-position array (the import
+            // convention of multi_setup)
+            multi_export_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(
+                h->X, ctl.pos_base[ctl.step & 1], B.slot_energy);
+            CUDA_TRY(h, cudaGetLastError());
+        }
         CUDA_TRY(h, cudaMemcpyAsync(slot_energy, B.slot_energy,
                                     B.cap * sizeof(double),
                                     cudaMemcpyDeviceToHost, h->stream));
+    }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return QMCB_OK;
 }
@@ -1762,6 +1903,15 @@ int qmcb_comm_init(qmcb_handle *h, const uint8_t *id, int32_t world_size,
     NCCL_TRY(h, api->CommInitRank(&h->comm, world_size, uid, rank));
     h->world = world_size;
     h->rank = rank;
+    if (h->dmc_ready) {
+        // a population loaded before the communicator existed: switch to
+        // the sharded weight path now
+        h->C.defer_weight = h->dp.energy_mode == 0 ? 1 : 0;
+        h->multi_ready = false;
+        drop_block_graph(h);
+    }
+    if (const char *e = getenv("QMCB_REBALANCE_EVERY"))
+        h->rebalance_every = atoll(e);
     CUDA_TRY(h, cudaMalloc(&h->d_counts, world_size * sizeof(long long)));
     // NCCL sets its peer-to-peer channels up lazily, on the first send/recv
     // of every (source, destination) pair, and that costs tens of
@@ -1774,15 +1924,23 @@ int qmcb_comm_init(qmcb_handle *h, const uint8_t *id, int32_t world_size,
     CUDA_TRY(h, cudaMalloc(&d_tmp, 2 * world_size * sizeof(long long)));
     CUDA_TRY(h, cudaMemsetAsync(d_tmp, 0, 2 * world_size * sizeof(long long),
                                 h->stream));
+    auto warm = [&]() -> int {
+        for (int p = 0; p < world_size; ++p) {
+            if (p == rank) continue;
+            NCCL_TRY(h, api->Send(h->d_counts + rank, 1, ncclInt64, p,
+                                  h->comm, h->stream));
+            NCCL_TRY(h, api->Recv(d_tmp + p, 1, ncclInt64, p, h->comm,
+                                  h->stream));
+        }
+        return QMCB_OK;
+    };
     NCCL_TRY(h, api->GroupStart());
-    for (int p = 0; p < world_size; ++p) {
-        if (p == rank) continue;
-        NCCL_TRY(h, api->Send(h->d_counts + rank, 1, ncclInt64, p, h->comm,
-                              h->stream));
-        NCCL_TRY(h, api->Recv(d_tmp + p, 1, ncclInt64, p, h->comm,
-                              h->stream));
+    {
+        int wrc = warm();
+        ncclResult_t ge = api->GroupEnd();
+        if (wrc) return wrc;
+        NCCL_TRY(h, ge);
     }
-    NCCL_TRY(h, api->GroupEnd());
     NCCL_TRY(h, api->AllReduce(d_tmp + world_size, d_tmp + world_size, 2,
                                ncclDouble, ncclSum, h->comm, h->stream));
     NCCL_TRY(h, api->AllGather(h->d_counts + rank, h->d_counts, 1, ncclInt64,
@@ -1895,50 +2053,60 @@ int qmcb_dmc_rebalance(qmcb_handle *h, int64_t *moved)
     double *s_energy = s_confs + (size_t) new_n * row;
     double *s_weight = s_energy + new_n;
     long long sent = 0;
-    NCCL_TRY(h, api->GroupStart());
-    for (int p = 0; p < R; ++p) {
-        // my current walkers that p will own
-        if (plan_send[2 * p + 1] > 0) {
-            long long src = plan_send[2 * p], n = plan_send[2 * p + 1];
-            if (p == me) {
-                long long dst = plan_recv[2 * p];
-                CUDA_TRY(h, cudaMemcpyAsync(
-                                s_confs + dst * row,
-                                B.confs[par] + src * row,
-                                n * row * sizeof(double),
-                                cudaMemcpyDeviceToDevice, h->stream));
-                CUDA_TRY(h, cudaMemcpyAsync(s_energy + dst,
-                                            B.energy[par] + src,
-                                            n * sizeof(double),
-                                            cudaMemcpyDeviceToDevice,
-                                            h->stream));
-                CUDA_TRY(h, cudaMemcpyAsync(s_weight + dst,
-                                            B.weight[par] + src,
-                                            n * sizeof(double),
-                                            cudaMemcpyDeviceToDevice,
-                                            h->stream));
-            } else {
-                NCCL_TRY(h, api->Send(B.confs[par] + src * row, n * row,
+    // every call between GroupStart and GroupEnd is checked, but a failure
+    // must not leave the group open (the peers would hang in theirs)
+    auto exchange = [&]() -> int {
+        for (int p = 0; p < R; ++p) {
+            // my current walkers that p will own
+            if (plan_send[2 * p + 1] > 0) {
+                long long src = plan_send[2 * p], n = plan_send[2 * p + 1];
+                if (p == me) {
+                    long long dst = plan_recv[2 * p];
+                    CUDA_TRY(h, cudaMemcpyAsync(
+                                    s_confs + dst * row,
+                                    B.confs[par] + src * row,
+                                    n * row * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, h->stream));
+                    CUDA_TRY(h, cudaMemcpyAsync(s_energy + dst,
+                                                B.energy[par] + src,
+                                                n * sizeof(double),
+                                                cudaMemcpyDeviceToDevice,
+                                                h->stream));
+                    CUDA_TRY(h, cudaMemcpyAsync(s_weight + dst,
+                                                B.weight[par] + src,
+                                                n * sizeof(double),
+                                                cudaMemcpyDeviceToDevice,
+                                                h->stream));
+                } else {
+                    NCCL_TRY(h, api->Send(B.confs[par] + src * row, n * row,
+                                          ncclDouble, p, h->comm, h->stream));
+                    NCCL_TRY(h, api->Send(B.energy[par] + src, n, ncclDouble,
+                                          p, h->comm, h->stream));
+                    NCCL_TRY(h, api->Send(B.weight[par] + src, n, ncclDouble,
+                                          p, h->comm, h->stream));
+                    sent += n;
+                }
+            }
+            // walkers of p that I will own
+            if (p != me && plan_recv[2 * p + 1] > 0) {
+                long long dst = plan_recv[2 * p], n = plan_recv[2 * p + 1];
+                NCCL_TRY(h, api->Recv(s_confs + dst * row, n * row,
                                       ncclDouble, p, h->comm, h->stream));
-                NCCL_TRY(h, api->Send(B.energy[par] + src, n, ncclDouble, p,
+                NCCL_TRY(h, api->Recv(s_energy + dst, n, ncclDouble, p,
                                       h->comm, h->stream));
-                NCCL_TRY(h, api->Send(B.weight[par] + src, n, ncclDouble, p,
+                NCCL_TRY(h, api->Recv(s_weight + dst, n, ncclDouble, p,
                                       h->comm, h->stream));
-                sent += n;
             }
         }
-        // walkers of p that I will own
-        if (p != me && plan_recv[2 * p + 1] > 0) {
-            long long dst = plan_recv[2 * p], n = plan_recv[2 * p + 1];
-            NCCL_TRY(h, api->Recv(s_confs + dst * row, n * row, ncclDouble, p,
-                                  h->comm, h->stream));
-            NCCL_TRY(h, api->Recv(s_energy + dst, n, ncclDouble, p, h->comm,
-                                  h->stream));
-            NCCL_TRY(h, api->Recv(s_weight + dst, n, ncclDouble, p, h->comm,
-                                  h->stream));
-        }
+        return QMCB_OK;
+    };
+    NCCL_TRY(h, api->GroupStart());
+    rc = exchange();
+    {
+        ncclResult_t ge = api->GroupEnd();
+        if (rc) return rc;
+        NCCL_TRY(h, ge);
     }
-    NCCL_TRY(h, api->GroupEnd());
     CUDA_TRY(h, cudaMemcpyAsync(B.confs[par], s_confs,
                                 new_n * row * sizeof(double),
                                 cudaMemcpyDeviceToDevice, h->stream));
@@ -1950,6 +2118,13 @@ int qmcb_dmc_rebalance(qmcb_handle *h, int64_t *moved)
                                 cudaMemcpyDeviceToDevice, h->stream));
     int w = (int) new_n;
     CUDA_TRY(h, cudaMemcpyAsync(&B.ctl->W_prev, &w, sizeof w,
+                                cudaMemcpyHostToDevice, h->stream));
+    // the walkers keep their global positions (the exchange preserves the
+    // order); this rank's slab now starts at another one
+    long long total = 0, base = 0;
+    for (int p = 0; p < R; ++p) total += cnt[p];
+    base = total * me / R;
+    CUDA_TRY(h, cudaMemcpyAsync(&B.ctl->pos_base[par], &base, sizeof base,
                                 cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (moved) *moved = sent;

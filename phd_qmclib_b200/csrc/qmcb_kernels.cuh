@@ -147,6 +147,12 @@ struct DmcCtl {
     long long tcur;             // time step the step kernel in flight works
                                 // on (set by branch_fill_kernel, so that the
                                 // population control may run next to it)
+    long long pos_base[2];      // global position (index in the ordered
+                                // concatenation of all ranks' slabs) of local
+                                // slot 0 of the population step t branches
+                                // from: pos_base[t & 1].  It keys the RNG, so
+                                // a sharded run draws the numbers of the
+                                // single-rank run
 };
 
 struct DmcBufs {
@@ -167,8 +173,28 @@ struct DmcBufs {
 struct DmcConsts {
     double dt, sigma, z_min, size, nwc_over_dt, target;
     uint64_t seed;
-    long long slot_offset;      // global index of local slot 0
+    long long slot_offset;      // global index of local slot 0 at start
     int energy_mode;
+    int defer_weight;           // sharded runs with energy_mode 0: the step
+                                // kernel leaves the branching weight to
+                                // multi_weight_kernel (the stale-slot energy
+                                // is indexed by GLOBAL position, known once
+                                // the counts of all ranks are)
+};
+
+// Sharded runs (one rank per GPU).  The reference's per-slot array behind
+// quirk Q1 (qmc_base/jastrow/dmc.py:810,936) is indexed by the position of
+// a walker in the ONE ordered ensemble; here every rank keeps a replica of
+// that global array and the ranks exchange, once per step, the slab of
+// values each of them writes (an all-gather of 8 bytes per slot that runs
+// next to the step kernel).
+struct DmcMulti {
+    double *aglob;          // [R * cap]  A[global position]
+    double *slab;           // [cap]      E_prev[parent] of my children
+    double *gathered;       // [R * cap]  the slabs of all ranks
+    double *vred;           // [R + 2]    {sum E, W, W_0 .. W_{R-1}}
+    long long *offs;        // [R + 1]    first global position of rank q
+    int R, rank, cap;
 };
 
 struct DmcLog {
@@ -265,6 +291,7 @@ branch_count_kernel(DmcBufs B, DmcConsts C)
     const int Wp = ctl->W_prev;
     const int par = (int) (ctl->step & 1);
     const uint32_t step = (uint32_t) ctl->step;
+    const long long pos0 = ctl->pos_base[par];
     const double *w = B.weight[par];
     long long local = 0;
     int base = blockIdx.x * BR_TILE + threadIdx.x * BR_ITEMS;
@@ -274,7 +301,7 @@ branch_count_kernel(DmcBufs B, DmcConsts C)
         int c = 0;
         if (s < Wp) {
             double u0, u1;
-            rng_uniform2(C.seed, (uint32_t) (C.slot_offset + s), 0u, step,
+            rng_uniform2(C.seed, (uint32_t) (pos0 + s), 0u, step,
                          STREAM_BRANCH, u0, u1);
             double x = w[s] + u0;
             c = (x >= (double) B.cap) ? B.cap : (int) x;
@@ -516,9 +543,18 @@ dmc_step_kernel(const __grid_constant__ DevModel M, GroupGeom geom, DmcBufs B,
         load4(pc, x.I, nvalid, vec_ok, zp);
         load4(pc + N, x.I, nvalid, vec_ok, fp);
         double nrm[TB];
-        const uint32_t gs = (uint32_t) (C.slot_offset + s);
-        rng_normal4<FAST>(M.tt, C.seed, gs, (uint32_t) x.I, (uint32_t) t,
-                          STREAM_DIFFUSE, nrm);
+        // the normals of a child are keyed by its PARENT's global position
+        // and by which of the parent's copies it is: both are known without
+        // this step's collective, and do not depend on how the ensemble is
+        // cut into ranks
+        int clone = 0;
+        while (clone < 0xffff && s - clone - 1 >= 0
+               && B.ref[s - clone - 1] == r)
+            ++clone;
+        const uint32_t gp = (uint32_t) (ctl->pos_base[par] + r);
+        rng_normal4<FAST>(M.tt, C.seed, gp,
+                          (uint32_t) x.I | ((uint32_t) clone << 16),
+                          (uint32_t) t, STREAM_DIFFUSE, nrm);
 #pragma unroll
         for (int c = 0; c < TB; ++c) {
             double zn = zp[c] + 2.0 * fp[c] * C.dt + C.sigma * nrm[c];
@@ -534,14 +570,117 @@ dmc_step_kernel(const __grid_constant__ DevModel M, GroupGeom geom, DmcBufs B,
         double *nc = nconfs + s * 2 * N;
         store4(nc + N, x.I, nvalid, vec_ok, o.F);
         if (x.I == 0) {
-            double e_parent = penergy[r];
-            double e_old = (C.energy_mode == 0) ? B.slot_energy[s] : e_parent;
-            double mean = (o.energy + e_old) / 2;
             nenergy[s] = o.energy;
-            nweight[s] = exp(-C.dt * (mean - eref));
-            B.slot_energy[s] = e_parent;
+            if (!C.defer_weight) {
+                double e_parent = penergy[r];
+                double e_old = (C.energy_mode == 0) ? B.slot_energy[s]
+                                                    : e_parent;
+                double mean = (o.energy + e_old) / 2;
+                nweight[s] = exp(-C.dt * (mean - eref));
+                B.slot_energy[s] = e_parent;
+            }
         }
     }
+}
+
+// --- sharded runs -----------------------------------------------------------
+// After branch_fill_kernel (finalize = 0): this rank's contribution to the
+// per-step collectives.
+__global__ void multi_pack_kernel(DmcBufs B, DmcMulti X, int with_slab)
+{
+    const DmcCtl *ctl = B.ctl;
+    const int W = ctl->W;
+    const int par = (int) (ctl->step & 1);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (with_slab && i < X.cap)
+        X.slab[i] = (i < W) ? B.energy[par][B.ref[i]] : 0.0;
+    if (i == 0) {
+        X.vred[0] = ctl->red[0];
+        X.vred[1] = ctl->red[1];
+        for (int q = 0; q < X.R; ++q)
+            X.vred[2 + q] = (q == X.rank) ? (double) W : 0.0;
+    }
+}
+
+// After the all-reduce of vred: global sums -> population control, and the
+// global positions of every rank's children.
+__global__ void multi_finalize_kernel(DmcBufs B, DmcConsts C, DmcLog L,
+                                      DmcMulti X)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    DmcCtl *ctl = B.ctl;
+    ctl->red[0] = X.vred[0];
+    ctl->red[1] = X.vred[1];
+    long long o = 0;
+    for (int q = 0; q < X.R; ++q) {
+        X.offs[q] = o;
+        o += (long long) (X.vred[2 + q] + 0.5);
+    }
+    X.offs[X.R] = o;
+    const long long t = ctl->step;
+    // this step's children are the parents of the next one
+    ctl->pos_base[(t + 1) & 1] = X.offs[X.rank];
+    dmc_finalize(B, C, L);
+}
+
+// Branching weight of this rank's children from the GLOBAL stale-slot array
+// (qmc_base/jastrow/dmc.py:810,820-821).  Runs after the step kernel.
+__global__ void multi_weight_kernel(DmcBufs B, DmcConsts C, DmcMulti X)
+{
+    const DmcCtl *ctl = B.ctl;
+    const int W = ctl->W;
+    const long long t = ctl->tcur;
+    const int par = (int) (t & 1);
+    const double eref = ctl->eref[par];
+    const long long base = X.offs[X.rank];
+    const long long asize = (long long) X.R * X.cap;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < W;
+         s += gridDim.x * blockDim.x) {
+        const long long p = base + s;
+        const double e_old = p < asize ? X.aglob[p] : 0.0;
+        const double mean = (B.energy[par ^ 1][s] + e_old) / 2;
+        B.weight[par ^ 1][s] = exp(-C.dt * (mean - eref));
+    }
+}
+
+// A[position] <- E_prev[parent] for the children of every rank
+// (qmc_base/jastrow/dmc.py:936); positions beyond the population keep their
+// values, like the reference's dead slots.
+__global__ void multi_apply_kernel(DmcMulti X)
+{
+    const long long total = (long long) X.R * X.cap;
+    for (long long idx = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+         idx < total; idx += (long long) gridDim.x * blockDim.x) {
+        const int q = (int) (idx / X.cap);
+        const long long i = idx - (long long) q * X.cap;
+        const long long o = X.offs[q];
+        if (i < X.offs[q + 1] - o && o + i < total)
+            X.aglob[o + i] = X.gathered[idx];
+    }
+}
+
+// The part of the global array beyond the live population, which the last
+// rank's local array carries on import (restart / initial state).
+__global__ void multi_tail_kernel(DmcMulti X, long long n_last)
+{
+    const long long total = (long long) X.R * X.cap;
+    const long long T = X.offs[X.R];
+    const double *src = X.gathered + (long long) (X.R - 1) * X.cap;
+    for (long long i = n_last + blockIdx.x * (long long) blockDim.x
+                       + threadIdx.x;
+         i < X.cap; i += (long long) gridDim.x * blockDim.x) {
+        const long long p = T + (i - n_last);
+        if (p < total) X.aglob[p] = src[i];
+    }
+}
+
+// Local view of the global array for export: out[i] = A[base + i].
+__global__ void multi_export_kernel(DmcMulti X, long long base, double *out)
+{
+    const long long total = (long long) X.R * X.cap;
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+         i < X.cap; i += (long long) gridDim.x * blockDim.x)
+        out[i] = base + i < total ? X.aglob[base + i] : 0.0;
 }
 
 // Gather of the yielded ("actual") population: slot s <- parent ref[s].

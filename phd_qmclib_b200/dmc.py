@@ -187,8 +187,16 @@ core_funcs = CoreFuncs()
 
 
 def local_capacity(max_num_walkers: int, world_size: int) -> int:
-    """Slots per rank when ``max_num_walkers`` global slots are sharded."""
-    return -(-int(max_num_walkers) // int(world_size))
+    """Slots per rank when ``max_num_walkers`` global slots are sharded.
+
+    The reference truncates the population at the GLOBAL capacity only
+    (qmc_base/dmc.py:636-651); a rank's share of the ensemble fluctuates more
+    than the whole between two rebalances, so every slab gets a quarter more
+    slots than its even share (and never fewer than 32 on top)."""
+    share = -(-int(max_num_walkers) // int(world_size))
+    if int(world_size) == 1:
+        return share
+    return share + max(32, share // 4)
 
 
 def slab_bounds(n: int, world_size: int, rank: int) -> t.Tuple[int, int]:
@@ -444,6 +452,31 @@ class Sampling:
         if self.reblock_max_order is not None:
             self.engine.dmc_reblock_reset(self.reblock_max_order)
 
+    def _check_capacity(self):
+        """The reference drops walkers silently when the population hits
+        ``max_num_walkers`` (qmc_base/dmc.py:636-651); here the
+        event is counted on the device and reported once per occurrence --
+        on a sharded run it means a SLAB hit its local capacity, which the
+        reference has no analogue of."""
+        hits = int(self.engine.dmc_scalars().capacity_hits)
+        seen = self._cache.get('capacity_hits', 0)
+        if hits > seen:
+            import warnings
+            where = (f'rank {self.rank}: local capacity '
+                     f'{self.local_capacity}' if self.world_size > 1 else
+                     f'max_num_walkers = {self.max_num_walkers}')
+            warnings.warn(f'DMC population truncated at capacity in '
+                          f'{hits - seen} time step(s) ({where}); raise '
+                          f'max_num_walkers or lower the time step',
+                          RuntimeWarning, stacklevel=3)
+        self._cache['capacity_hits'] = hits
+
+    @property
+    def capacity_hits(self) -> int:
+        """Time steps (since the iterator started) in which branching was
+        truncated at the capacity of this rank."""
+        return int(self.engine.dmc_scalars().capacity_hits)
+
     def otf_reblock_data(self) -> t.Dict[str, np.ndarray]:
         """Accumulated on-the-fly reblocking tables of the per-step series
         (energy, weight, num_walkers, ref_energy, accum_energy) of every
@@ -536,12 +569,9 @@ class Sampling:
                 nts, eval_estimators=est, out=out,
                 density=None if dp.assume_none else i_den,
                 ssf=None if sp.assume_none else i_ssf)
-            if self.world_size > 1 and est:
-                # the engine returns this rank's partial sums
-                allreduce_sum(self.dist,
-                              [a for a, none in ((i_den, dp.assume_none),
-                                                 (i_ssf, sp.assume_none))
-                               if not none])
+            # (sharded: the engine has summed the estimator tables over the
+            # ranks on the device, over its own NCCL communicator)
+            self._check_capacity()
             stamp = self._cache['stamp'] = object()
             blk = SamplingBlock(props, i_den, i_ssf,
                                 lambda s=stamp: self._fetch_state(s))

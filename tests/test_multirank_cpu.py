@@ -139,7 +139,8 @@ def _sampling_worker(rank, world, port, q):
                            ssf_est_spec=dmc.SSFEstSpec(4))
         assert (smp.world_size, smp.rank) == (world, rank)
         cap = smp.local_capacity
-        assert cap == -(-101 // world)
+        share = -(-101 // world)
+        assert cap == share + max(32, share // 4)
         assert smp.state_confs_shape == (cap, 2, 16)
         assert smp._engine_params().local_capacity == cap
         lo, hi = dmc.slab_bounds(64, world, rank)
@@ -199,7 +200,8 @@ def test_sampling_sharded_needs_a_seed():
     with pytest.raises(ValueError):
         dmc.Sampling(spec, 1e-3, 100, 64, dist=_Dist)
     smp = dmc.Sampling(spec, 1e-3, 100, 64, rng_seed=1, dist=_Dist)
-    assert smp.local_capacity == 25 and smp.state_props_shape == (25,)
+    assert smp.local_capacity == 25 + 32
+    assert smp.state_props_shape == (57,)
     assert [dmc.slab_bounds(10, 4, r) for r in range(4)] == [
         (0, 3), (3, 6), (6, 8), (8, 10)]
 

@@ -76,6 +76,10 @@ class OracleEngine:
         self.last = it
         return out
 
+    def dmc_scalars(self):
+        from phd_qmclib_b200 import _lib
+        return _lib.StateScalars()
+
     def dmc_get_state(self, want_confs=True):
         from phd_qmclib_b200 import _lib
         st, it = self.st, self.last
