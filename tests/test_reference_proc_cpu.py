@@ -1,6 +1,6 @@
-"""CPU, builder container only: the UNCHANGED reference procedure layer
-(qmc_exec.dmc.Proc.exec / qmc_exec.vmc.Proc.exec, imported from
-/root/reference through oracle/refshim.py) drives this package's sampler
+"""CPU: the UNCHANGED reference procedure layer (qmc_exec.dmc.Proc.exec /
+qmc_exec.vmc.Proc.exec, imported from /root/reference or baseline/_ref
+through oracle/refshim.py) drives this package's sampler
 classes through the injection point INTEGRATION.md documents -- a subclass
 overriding the `sampling` cached_property.
 
@@ -13,8 +13,12 @@ import os
 import numpy as np
 import pytest
 
-REF = '/root/reference/src/phd_qmclib'
-pytestmark = pytest.mark.skipif(not os.path.isdir(REF),
+import sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(
+    os.path.abspath(__file__))), 'oracle'))
+import refshim  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not refshim.available(),
                                 reason='reference tree not present')
 
 
