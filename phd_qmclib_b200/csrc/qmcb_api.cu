@@ -37,6 +37,7 @@ struct NcclApi {
     void *dl = nullptr;
     decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommInitRankConfig) CommInitRankConfig = nullptr;  // optional
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
     decltype(&ncclAllGather) AllGather = nullptr;
@@ -78,6 +79,8 @@ static NcclApi *nccl_api()
     QMCB_NCCL_SYM(GroupStart) QMCB_NCCL_SYM(GroupEnd)
     QMCB_NCCL_SYM(GetErrorString)
 #undef QMCB_NCCL_SYM
+    api.CommInitRankConfig = (decltype(api.CommInitRankConfig)) dlsym(
+        api.dl, "ncclCommInitRankConfig");
     return &api;
 }
 
@@ -155,6 +158,7 @@ struct qmcb_handle {
     cudaStream_t pc_stream = nullptr;   // all-reduce + population control of
     cudaEvent_t ev_branched = nullptr;  // a step run here, next to the step
     cudaEvent_t ev_controlled = nullptr;    // kernel (which needs neither)
+    cudaEvent_t ev_weighted = nullptr;
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
     long long *d_counts = nullptr;      // [world] live walkers per rank
@@ -966,6 +970,7 @@ void qmcb_destroy(qmcb_handle *h)
     }
     if (h->ev_branched) cudaEventDestroy(h->ev_branched);
     if (h->ev_controlled) cudaEventDestroy(h->ev_controlled);
+    if (h->ev_weighted) cudaEventDestroy(h->ev_weighted);
     if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
     for (auto ev : h->step_ev) cudaEventDestroy(ev);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1492,7 +1497,13 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
             if (glob_a) {
                 const int grid = h->sm_count * 4;
                 multi_weight_kernel<<<grid, 256, 0, h->stream>>>(B, h->C, X);
-                multi_apply_kernel<<<grid, 256, 0, h->stream>>>(X);
+                // the update of the global array is off the critical path:
+                // the next reader is the next step's weight kernel, behind
+                // the next ev_controlled of this same stream
+                CUDA_TRY(h, cudaEventRecord(h->ev_weighted, h->stream));
+                CUDA_TRY(h, cudaStreamWaitEvent(h->pc_stream, h->ev_weighted,
+                                                0));
+                multi_apply_kernel<<<grid, 256, 0, h->pc_stream>>>(X);
             }
         }
         return QMCB_OK;
@@ -1539,12 +1550,14 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
             if (rc) return rc;
             est_launches += 3;
         }
-        // Sharded runs without per-slot estimator state: every
+        // Sharded runs without per-slot estimator state (the forward-walking
+        // rows of pure S(k), the bin lists of the density): every
         // `rebalance_every` steps look at the counts of all ranks (one
         // 8 (R + 1)-byte read) and even the slabs out when they have drifted
         // apart by more than 2 %, or when one of them nears its capacity
         // (the reference truncates at the GLOBAL capacity only).
-        if (h->comm && !do_ssf && !do_den && h->rebalance_every > 0
+        if (h->comm && !do_den && (!do_ssf || !h->dp.ssf_as_pure)
+            && h->rebalance_every > 0
             && (i + 1) % h->rebalance_every == 0 && i + 1 < nts) {
             std::vector<long long> offs(X.R + 1);
             CUDA_TRY(h, cudaMemcpyAsync(offs.data(), X.offs,
@@ -1564,6 +1577,12 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
                 h->rebalanced_in_block += mv;
             }
         }
+    }
+    if (h->comm) {
+        // the control stream's last update of the global array is part of
+        // this block
+        CUDA_TRY(h, cudaEventRecord(h->ev_controlled, h->pc_stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_controlled, 0));
     }
     if (h->comm && (do_den || do_ssf)) {
         // the tables hold this rank's partial sums: global sums on the
@@ -1900,7 +1919,23 @@ int qmcb_comm_init(qmcb_handle *h, const uint8_t *id, int32_t world_size,
     CUDA_TRY(h, cudaSetDevice(h->device));
     ncclUniqueId uid;
     memcpy(&uid, id, sizeof uid);
-    NCCL_TRY(h, api->CommInitRank(&h->comm, world_size, uid, rank));
+    // The per-step collectives are a few KB to ~1 MB and run NEXT TO the step
+    // kernel, which fills every SM: keep NCCL's kernels small (few CTAs) so
+    // that they fit into the resources one retiring step CTA frees.
+    bool made = false;
+    if (api->CommInitRankConfig && !getenv("QMCB_NCCL_DEFAULT_CONFIG")) {
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.minCTAs = 1;
+        cfg.maxCTAs = 4;
+        if (const char *e = getenv("QMCB_NCCL_MAX_CTAS"))
+            cfg.maxCTAs = std::max(1, atoi(e));
+        ncclResult_t r = api->CommInitRankConfig(&h->comm, world_size, uid,
+                                                 rank, &cfg);
+        made = r == ncclSuccess;
+        if (!made) h->comm = nullptr;
+    }
+    if (!made)
+        NCCL_TRY(h, api->CommInitRank(&h->comm, world_size, uid, rank));
     h->world = world_size;
     h->rank = rank;
     if (h->dmc_ready) {
@@ -1947,8 +1982,15 @@ int qmcb_comm_init(qmcb_handle *h, const uint8_t *id, int32_t world_size,
                                h->comm, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaFree(d_tmp));
-    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->pc_stream,
-                                          cudaStreamNonBlocking));
+    // highest priority: the block scheduler places the (small) collective
+    // and population-control kernels ahead of the step kernel's queue of
+    // CTAs instead of after it
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_TRY(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CUDA_TRY(h, cudaStreamCreateWithPriority(&h->pc_stream,
+                                             cudaStreamNonBlocking, prio_hi));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_weighted,
+                                         cudaEventDisableTiming));
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_branched,
                                          cudaEventDisableTiming));
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_controlled,

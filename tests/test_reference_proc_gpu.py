@@ -96,6 +96,7 @@ def test_reference_vmc_proc_exec_on_the_gpu(ref):
     assert blocks.energy.totals.shape == (6,)
     assert 14.0 < blocks.energy.mean / 16 < 19.0
     assert blocks.ss_factor.fdk_sqr_abs_part.totals.shape == (6, 8)
+    # block means of |rho_0|^2 = N^2
     assert np.allclose(blocks.ss_factor.fdk_sqr_abs_part.totals[:, 0],
-                       16.0 ** 2 * 256, rtol=1e-12)
+                       16.0 ** 2, rtol=1e-12)
     assert result.state.sys_conf.shape == (2, 16)
