@@ -405,6 +405,29 @@ def cpu_baseline_subprocess(name):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run on the host cores next to that GPU (NVML's
+    CPU affinity of the device), so that the pinned staging buffers of the
+    end-to-end leg are first touched on the GPU's own NUMA node instead of
+    all eight processes sharing one node's memory and PCIe root."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hdl = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(hdl, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64)
+                if (m >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f'{len(cpus)} cores next to GPU {index}'
+    except Exception as exc:        # noqa: BLE001 - best effort
+        return f'not bound ({exc.__class__.__name__})'
+    return 'not bound'
+
+
 class Dist:
     """torch.distributed plumbing of the bench (barrier, max/sum over ranks)."""
 
@@ -419,6 +442,8 @@ class Dist:
                              'fallback for the product arm; use --impl '
                              'reference)')
         torch.cuda.set_device(self.local)
+        self.affinity = bind_to_gpu_numa_node(self.local) \
+            if self.world > 1 else None
         self.dist = None
         if self.world > 1:
             import torch.distributed as dist
@@ -688,6 +713,7 @@ def run_dmc(name, cfg, args, D):
         'roofline': roofline, 'e2e': e2e, 'gpu_launches': int(launches),
         'clocks': clocks, 'per_rank': per_rank,
         'rebalanced_walkers_rank0': int(moved), 'capacity_hits_rank0': hits,
+        'host_affinity_rank0': D.affinity,
         'l2_flush': flush is not None,
         'lib': os.path.relpath(_lib.LIB_PATH, ROOT),
     }
