@@ -320,6 +320,16 @@ QMCB_API int qmcb_vmc_run_block(qmcb_handle *h, int64_t ns, double *lnpsi,
                                 double *energy, uint8_t *move_stat,
                                 double *ssf, double *accept_rate,
                                 double *sum_energy, double *sum_ssf);
+/* The same chain with EVERY state kept (reference `as_chain` /
+ * `state_data_blocks`, qmc_base/vmc.py:773-902: confs (ns, 2, N) per chain,
+ * used e.g. to seed a DMC run): one launch for the ns steps, the
+ * configurations recorded on the device and shipped once.
+ * confs [C][ns][2][N] (row 0 positions, row 1 drift); the other outputs as in
+ * qmcb_vmc_run_block, each may be NULL except confs. */
+QMCB_API int qmcb_vmc_run_chain(qmcb_handle *h, int64_t ns, double *lnpsi,
+                                double *energy, uint8_t *move_stat,
+                                double *confs, double *accept_rate);
+
 /* Current configurations [C][2][N] and ln|Psi| [C] (last_state). */
 QMCB_API int qmcb_vmc_get_state(qmcb_handle *h, double *confs, double *lnpsi);
 

@@ -25,6 +25,7 @@ SYMBOLS = [
     'qmcb_one_body_density', 'qmcb_one_body_density_device',
     'qmcb_fourier_density_k', 'qmcb_set_model_params', 'qmcb_cs_load',
     'qmcb_cs_variance', 'qmcb_dmc_reblock_reset', 'qmcb_dmc_reblock_get',
+    'qmcb_vmc_run_chain',
 ]
 
 
@@ -126,6 +127,7 @@ def load():
     L.qmcb_rebalance_plan.argtypes = [vp, i32, i32, vp, vp, C.POINTER(i64)]
     L.qmcb_vmc_init.argtypes = [vp, C.POINTER(VMCParams), vp, i64]
     L.qmcb_vmc_run_block.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp]
+    L.qmcb_vmc_run_chain.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.qmcb_vmc_get_state.argtypes = [vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)

@@ -2244,10 +2244,33 @@ int qmcb_vmc_init(qmcb_handle *h, const qmcb_vmc_params *params,
     return QMCB_OK;
 }
 
+static int vmc_run_block_impl(qmcb_handle *h, int64_t ns, double *lnpsi,
+                              double *energy, uint8_t *move_stat, double *ssf,
+                              double *accept_rate, double *sum_energy,
+                              double *sum_ssf, double *confs);
+
 int qmcb_vmc_run_block(qmcb_handle *h, int64_t ns, double *lnpsi,
                        double *energy, uint8_t *move_stat, double *ssf,
                        double *accept_rate, double *sum_energy,
                        double *sum_ssf)
+{
+    return vmc_run_block_impl(h, ns, lnpsi, energy, move_stat, ssf,
+                              accept_rate, sum_energy, sum_ssf, nullptr);
+}
+
+int qmcb_vmc_run_chain(qmcb_handle *h, int64_t ns, double *lnpsi,
+                       double *energy, uint8_t *move_stat, double *confs,
+                       double *accept_rate)
+{
+    if (h && !confs) FAIL(h, QMCB_ERR_INVALID, "confs must not be null");
+    return vmc_run_block_impl(h, ns, lnpsi, energy, move_stat, nullptr,
+                              accept_rate, nullptr, nullptr, confs);
+}
+
+static int vmc_run_block_impl(qmcb_handle *h, int64_t ns, double *lnpsi,
+                              double *energy, uint8_t *move_stat, double *ssf,
+                              double *accept_rate, double *sum_energy,
+                              double *sum_ssf, double *confs)
 {
     if (!h) return QMCB_ERR_INVALID;
     if (!h->vmc_ready) FAIL(h, QMCB_ERR_STATE, "qmcb_vmc_init not called");
@@ -2262,7 +2285,12 @@ int qmcb_vmc_run_block(qmcb_handle *h, int64_t ns, double *lnpsi,
     size_t off_ln = bytes; if (lnpsi) bytes += n_ser * sizeof(double);
     size_t off_e = bytes; if (energy) bytes += n_ser * sizeof(double);
     size_t off_ssf = bytes; if (ssf) bytes += n_ser * M * 3 * sizeof(double);
-    size_t off_st = bytes; if (move_stat) bytes += n_ser;
+    size_t off_st = bytes; if (move_stat) bytes += (n_ser + 7) / 8 * 8;
+    const size_t conf_bytes = n_ser * 2 * (size_t) h->M.nop * sizeof(double);
+    size_t off_cf = bytes; if (confs) bytes += conf_bytes;
+    if (bytes > ((size_t) 64 << 30))
+        FAIL(h, QMCB_ERR_INVALID, "per-step series of this block exceed "
+                                  "64 GB: use fewer steps per call");
     int rc = ensure_scratch(h, bytes ? bytes : 8);
     if (rc) return rc;
     char *scr = reinterpret_cast<char *>(h->d_scratch);
@@ -2279,6 +2307,7 @@ int qmcb_vmc_run_block(qmcb_handle *h, int64_t ns, double *lnpsi,
     a.out_ssf = ssf ? reinterpret_cast<double *>(scr + off_ssf) : nullptr;
     a.out_stat = move_stat ? reinterpret_cast<unsigned char *>(scr + off_st)
                            : nullptr;
+    a.out_confs = confs ? reinterpret_cast<double *>(scr + off_cf) : nullptr;
     a.accept_rate = h->vmc_acc;
     a.sum_energy = h->vmc_sum_e;
     a.sum_ssf = (M && sum_ssf) ? h->vmc_sum_ssf : nullptr;
@@ -2309,6 +2338,7 @@ int qmcb_vmc_run_block(qmcb_handle *h, int64_t ns, double *lnpsi,
     if (energy) CUDA_TRY(h, d2h(energy, a.out_energy, n_ser * sizeof(double)));
     if (ssf) CUDA_TRY(h, d2h(ssf, a.out_ssf, n_ser * M * 3 * sizeof(double)));
     if (move_stat) CUDA_TRY(h, d2h(move_stat, a.out_stat, n_ser));
+    if (confs) CUDA_TRY(h, d2h(confs, a.out_confs, conf_bytes));
     if (accept_rate)
         CUDA_TRY(h, d2h(accept_rate, h->vmc_acc, C * sizeof(double)));
     if (sum_energy)

@@ -700,51 +700,68 @@ __device__ __forceinline__ void pair_diag(
     }
 }
 
-// A ragged tile of the drift / energy kernels: the row block and/or the
-// column block is the last, partly filled one (N not a multiple of 4), or the
-// tile is the diagonal of such a block.  Only the valid pairs are evaluated
-// (the bounds are the same for all lanes of a warp in the interleaved
-// mapping), so the thread that owns the ragged block does not become the
-// straggler every barrier waits for.
-__device__ __forceinline__ void pair_ragged(
+// Off-diagonal 4x4 tile of the drift / energy kernels (no ln|Psi|), with the
+// ragged last block (N not a multiple of 4) at full speed:
+//  * a ragged COLUMN block just ends the column loop early (`ncol` < 4): the
+//    lanes of a warp that meet another block idle for those iterations, no
+//    extra instruction is issued;
+//  * a ragged ROW block (the one thread per walker that owns it) nulls the
+//    reciprocal of its padding rows (two FSEL per pair; the numerators are
+//    finite, so t = num * 0 and 1/den^2 vanish).  ROWMASK is chosen per WARP
+//    (any lane owns a ragged block), so that the lanes of a warp never run
+//    two different tile routines one after the other -- that serialisation
+//    made the warp of the ragged block the straggler of every CTA barrier
+//    (N = 50: 1.09 ms per step against 0.83 ms for N = 52).
+template <bool ROWMASK>
+__device__ __forceinline__ void pair_tile_ef(
     const DevModel &M, const GroupSmem &sm, int g, int J, int qslot,
-    bool diag, int nvalid, int nvj, const double (&rsa)[TB],
-    const double (&rca)[TB], const double (&rsu)[TB],
-    const double (&rcu)[TB], PairAcc &acc)
+    int nvalid, int ncol, const double (&rsa)[TB], const double (&rca)[TB],
+    const double (&rsu)[TB], const double (&rcu)[TB], PairAcc &acc)
 {
     const int nbp = sm.nbp;
-    const unsigned vstride = 4u * (unsigned) nbp * (unsigned) sizeof(double2);
-    const double s_m = M.s_m_scaled, mu = M.mu;
+    const int cstride = nbp * (int) sizeof(double2);    // next column particle
+    const unsigned vstride = 4u * (unsigned) cstride;   // next variant
+    const char *pa1 = reinterpret_cast<const char *>(sm.a1(g, 0) + J);
+    const char *pv = reinterpret_cast<const char *>(sm.var(g, 0, 0) + J);
     double *pq = sm.q(g, qslot, 0) + J;
-    for (int c2 = 0; c2 < TB; ++c2) {
-        double fc = 0.0;
-        if (c2 < nvj) {
-            const double2 A1 = sm.a1(g, c2)[J];
-            const char *pv =
-                reinterpret_cast<const char *>(sm.var(g, 0, c2) + J);
+    const double s_m = M.s_m_scaled;
+    double2 A1 = *reinterpret_cast<const double2 *>(pa1);
+    const double mu = M.mu;
+#pragma unroll 1
+    for (int c2 = 0; c2 < ncol; ++c2) {
+        double den_f[TB], num_f[TB];
+        double2 V[TB];
 #pragma unroll
-            for (int c1 = 0; c1 < TB; ++c1) {
-                if (c1 < nvalid && (!diag || c1 < c2)) {
-                    const double den_f = fma(rsa[c1], A1.y, -(rca[c1] * A1.x));
-                    const double num_f =
-                        mu * fma(rca[c1], A1.y, rsa[c1] * A1.x);
-                    const unsigned hn = (unsigned) __double2hiint(num_f);
-                    const unsigned hd = (unsigned) __double2hiint(den_f);
-                    const unsigned v = ((hn >> 31) << 1) + (hd >> 31);
-                    const double2 V =
-                        *reinterpret_cast<const double2 *>(pv + v * vstride);
-                    const bool near = fabs(den_f) < s_m;
-                    const double num_n = fma(rsu[c1], V.y, -(rcu[c1] * V.x));
-                    const double den_n = fma(rcu[c1], V.y, rsu[c1] * V.x);
-                    const double num = near ? num_n : num_f;
-                    const double den = near ? den_n : den_f;
-                    const double inv = fast_rcp(den);
-                    const double t = num * inv;
-                    acc.T[c1] += t;
-                    fc -= t;
-                    acc.K = fma(inv, inv, acc.K);
-                }
-            }
+        for (int c1 = 0; c1 < TB; ++c1) {
+            den_f[c1] = fma(rsa[c1], A1.y, -(rca[c1] * A1.x));
+            num_f[c1] = mu * fma(rca[c1], A1.y, rsa[c1] * A1.x);
+        }
+#pragma unroll
+        for (int c1 = 0; c1 < TB; ++c1) {
+            unsigned hn = (unsigned) __double2hiint(num_f[c1]);
+            unsigned hd = (unsigned) __double2hiint(den_f[c1]);
+            unsigned v = ((hn >> 31) << 1) + (hd >> 31);
+            V[c1] = *reinterpret_cast<const double2 *>(pv + v * vstride);
+        }
+        if (c2 + 1 < ncol) {
+            pa1 += cstride;
+            A1 = *reinterpret_cast<const double2 *>(pa1);
+        }
+        pv += cstride;
+        double fc = 0.0;
+#pragma unroll
+        for (int c1 = 0; c1 < TB; ++c1) {
+            bool near = fabs(den_f[c1]) < s_m;
+            double num_n = fma(rsu[c1], V[c1].y, -(rcu[c1] * V[c1].x));
+            double den_n = fma(rcu[c1], V[c1].y, rsu[c1] * V[c1].x);
+            double num = near ? num_n : num_f[c1];
+            double den = near ? den_n : den_f[c1];
+            double inv = fast_rcp(den);
+            if (ROWMASK && c1 > 0) inv = (c1 < nvalid) ? inv : 0.0;
+            double t = num * inv;
+            acc.T[c1] += t;
+            fc -= t;
+            acc.K = fma(inv, inv, acc.K);
         }
         *pq = fc;
         pq += nbp;
@@ -856,7 +873,12 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
     const int k_last_row = (even && I >= kmax) ? kmax - 1 : kmax;
     const int k_skip_col = (even && I < kmax) ? kmax : -1;
     const int j_ragged = (M.nop % TB) ? nb - 1 : -1;
+    const int n_ragged = M.nop - TB * (nb - 1);     // particles of that block
     const bool row_ragged = nvalid < TB;
+    // one tile routine per warp (see pair_tile_ef); every thread of the CTA
+    // is here, active or not
+    const bool warp_rowmask =
+        diag_direct && __any_sync(0xffffffffu, pairs && row_ragged);
     for (int k0 = diag_direct ? 1 : 0; k0 <= kmax; k0 += kc) {
         const int k1 = min(k0 + kc, kmax + 1);
         if (pairs) {
@@ -865,10 +887,14 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
                 int J = I + k;
                 if (J >= nb) J -= nb;
                 const bool ragged = row_ragged || J == j_ragged;
-                if (!LN && (k == 0 || ragged)) {
-                    const int nvj = min(TB, M.nop - TB * J);
-                    pair_ragged(M, sm, g, J, k - k0, k == 0, nvalid, nvj,
-                                rsa, rca, rsu, rcu, acc);
+                if (diag_direct) {
+                    const int ncol = (J == j_ragged) ? n_ragged : TB;
+                    if (warp_rowmask)
+                        pair_tile_ef<true>(M, sm, g, J, k - k0, nvalid, ncol,
+                                           rsa, rca, rsu, rcu, acc);
+                    else
+                        pair_tile_ef<false>(M, sm, g, J, k - k0, nvalid, ncol,
+                                            rsa, rca, rsu, rcu, acc);
                 } else if (LN || k == 0 || ragged) {
                     const int nvj = min(TB, M.nop - TB * J);
                     pair_tile<LN, EF, true>(M, sm, g, J, k - k0, k == 0,

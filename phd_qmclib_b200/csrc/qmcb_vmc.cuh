@@ -37,6 +37,9 @@ struct VmcArgs {
     double *accept_rate;                // [C] or null
     double *sum_energy;                 // [C][2] (sum e, sum e^2) or null
     double *sum_ssf;                    // [C][M][3] or null
+    double *out_confs;                  // [C][ns][2][N] or null: every state
+                                        // of the chain (as_chain,
+                                        // qmc_base/vmc.py:773-902)
 };
 
 // FAST: node-table transcendentals (TrigTab); needs every position in
@@ -119,6 +122,11 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                 }
                 se += e_prev;
                 se2 = fma(e_prev, e_prev, se2);
+                if (a.out_confs) {
+                    double *oc = a.out_confs + ((c * a.ns + st) * 2) * N;
+                    store4(oc, x.I, nvalid, vec_ok, z);
+                    store4(oc + N, x.I, nvalid, vec_ok, Fcur);
+                }
                 if (x.I == 0) {
                     if (a.out_lnpsi) a.out_lnpsi[c * a.ns + st] = ln_cur;
                     if (a.out_energy) a.out_energy[c * a.ns + st] = e_prev;

@@ -469,6 +469,20 @@ class Engine:
         self._check(rc, 'qmcb_vmc_run_block')
         return out
 
+    def vmc_run_chain(self, ns):
+        """``ns`` steps with every state kept: dict(confs (C, ns, 2, N),
+        lnpsi, energy, move_stat (C, ns), accept_rate (C,)), one launch."""
+        c = self._vmc_chains
+        out = dict(confs=np.empty((c, ns, 2, self.nop)),
+                   lnpsi=np.empty((c, ns)), energy=np.empty((c, ns)),
+                   move_stat=np.empty((c, ns), dtype=np.uint8),
+                   accept_rate=np.empty(c))
+        rc = self._L.qmcb_vmc_run_chain(
+            self._h, ns, ptr(out['lnpsi']), ptr(out['energy']),
+            ptr(out['move_stat']), ptr(out['confs']), ptr(out['accept_rate']))
+        self._check(rc, 'qmcb_vmc_run_chain')
+        return out
+
     def vmc_get_state(self):
         c = self._vmc_chains
         confs, ln = np.empty((c, 2, self.nop)), np.empty(c)

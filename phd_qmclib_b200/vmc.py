@@ -285,15 +285,11 @@ class Sampling:
             yield self._chain_block(ns, single, nch, nop)
 
     def _chain_block(self, ns, single, nch, nop):
-        confs = np.zeros((nch, ns, 2, nop))
-        ln = np.zeros((nch, ns)); en = np.zeros((nch, ns))
-        stat = np.zeros((nch, ns), dtype=np.bool_)
-        for i in range(ns):
-            o = self.engine.vmc_run_block(1, series=True)
-            c, _ = self.engine.vmc_get_state()
-            confs[:, i] = c
-            ln[:, i] = o['lnpsi'][:, 0]; en[:, i] = o['energy'][:, 0]
-            stat[:, i] = o['move_stat'][:, 0]
+        # one launch: the kernel records every state of the chains on the
+        # device (qmcb_vmc_run_chain)
+        o = self.engine.vmc_run_chain(ns)
+        confs, ln, en = o['confs'], o['lnpsi'], o['energy']
+        stat = o['move_stat'].astype(np.bool_)
         acc = stat.mean(axis=1)
         last = self._last_state(single, stat[:, -1])
         if single:
