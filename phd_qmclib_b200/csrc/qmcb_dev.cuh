@@ -712,8 +712,10 @@ __device__ __forceinline__ void pair_diag(
 //    two different tile routines one after the other -- that serialisation
 //    made the warp of the ragged block the straggler of every CTA barrier
 //    (N = 50: 1.09 ms per step against 0.83 ms for N = 52).
-template <bool ROWMASK>
-__device__ __forceinline__ void pair_tile_ef(
+// FULL: the model has no ragged block at all (N a multiple of 4, a uniform
+// condition): compile-time column count.
+template <bool LN, bool EF, bool ROWMASK, bool FULL = false>
+__device__ __forceinline__ void pair_tile_lean(
     const DevModel &M, const GroupSmem &sm, int g, int J, int qslot,
     int nvalid, int ncol, const double (&rsa)[TB], const double (&rca)[TB],
     const double (&rsu)[TB], const double (&rcu)[TB], PairAcc &acc)
@@ -728,7 +730,7 @@ __device__ __forceinline__ void pair_tile_ef(
     double2 A1 = *reinterpret_cast<const double2 *>(pa1);
     const double mu = M.mu;
 #pragma unroll 1
-    for (int c2 = 0; c2 < ncol; ++c2) {
+    for (int c2 = 0; c2 < (FULL ? TB : ncol); ++c2) {
         double den_f[TB], num_f[TB];
         double2 V[TB];
 #pragma unroll
@@ -743,7 +745,7 @@ __device__ __forceinline__ void pair_tile_ef(
             unsigned v = ((hn >> 31) << 1) + (hd >> 31);
             V[c1] = *reinterpret_cast<const double2 *>(pv + v * vstride);
         }
-        if (c2 + 1 < ncol) {
+        if (c2 + 1 < (FULL ? TB : ncol)) {
             pa1 += cstride;
             A1 = *reinterpret_cast<const double2 *>(pa1);
         }
@@ -757,15 +759,32 @@ __device__ __forceinline__ void pair_tile_ef(
             double num = near ? num_n : num_f[c1];
             double den = near ? den_n : den_f[c1];
             double inv = fast_rcp(den);
-            if (ROWMASK && c1 > 0) inv = (c1 < nvalid) ? inv : 0.0;
-            double t = num * inv;
-            acc.T[c1] += t;
-            fc -= t;
-            acc.K = fma(inv, inv, acc.K);
+            if (ROWMASK && c1 > 0) {
+                const bool ok = c1 < nvalid;
+                inv = ok ? inv : 0.0;
+                if (LN) {
+                    den_f[c1] = ok ? den_f[c1] : 1.0;
+                    den_n = ok ? den_n : 1.0;
+                    acc.nnear += (ok && near) ? 1 : 0;
+                }
+            } else if (LN) {
+                acc.nnear += near ? 1 : 0;
+            }
+            if (EF) {
+                double t = num * inv;
+                acc.T[c1] += t;
+                fc -= t;
+                acc.K = fma(inv, inv, acc.K);
+            }
+            if (LN) {
+                acc.pf *= near ? 1.0 : fabs(den_f[c1]);
+                acc.pn *= near ? fabs(den_n) : 1.0;
+            }
         }
-        *pq = fc;
-        pq += nbp;
+        if (EF) { *pq = fc; pq += nbp; }
+        if (LN) { renorm(acc.pf, acc.ef); renorm(acc.pn, acc.en); }
     }
+    if (LN) acc.npair += FULL ? TB * TB : nvalid * ncol;
 }
 
 // Evaluate drift, local energy (EF) and/or ln|Psi| (LN) of G walkers held by
@@ -877,8 +896,7 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
     const bool row_ragged = nvalid < TB;
     // one tile routine per warp (see pair_tile_ef); every thread of the CTA
     // is here, active or not
-    const bool warp_rowmask =
-        diag_direct && __any_sync(0xffffffffu, pairs && row_ragged);
+    const bool warp_rowmask = __any_sync(0xffffffffu, pairs && row_ragged);
     for (int k0 = diag_direct ? 1 : 0; k0 <= kmax; k0 += kc) {
         const int k1 = min(k0 + kc, kmax + 1);
         if (pairs) {
@@ -886,24 +904,23 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
             for (int k = k0; k < ke; ++k) {
                 int J = I + k;
                 if (J >= nb) J -= nb;
-                const bool ragged = row_ragged || J == j_ragged;
-                if (diag_direct) {
-                    const int ncol = (J == j_ragged) ? n_ragged : TB;
-                    if (warp_rowmask)
-                        pair_tile_ef<true>(M, sm, g, J, k - k0, nvalid, ncol,
-                                           rsa, rca, rsu, rcu, acc);
-                    else
-                        pair_tile_ef<false>(M, sm, g, J, k - k0, nvalid, ncol,
-                                            rsa, rca, rsu, rcu, acc);
-                } else if (LN || k == 0 || ragged) {
-                    const int nvj = min(TB, M.nop - TB * J);
-                    pair_tile<LN, EF, true>(M, sm, g, J, k - k0, k == 0,
-                                            nvalid, nvj, rsa, rca, rsu, rcu,
-                                            acc);
+                const int ncol = (J == j_ragged) ? n_ragged : TB;
+                if (k == 0) {
+                    // the diagonal block of the ln|Psi| kernels: pairs
+                    // c1 < c2 only, through the generic masked tile
+                    pair_tile<LN, EF, true>(M, sm, g, J, k - k0, true, nvalid,
+                                            ncol, rsa, rca, rsu, rcu, acc);
+                } else if (j_ragged < 0) {
+                    pair_tile_lean<LN, EF, false, true>(
+                        M, sm, g, J, k - k0, TB, TB, rsa, rca, rsu, rcu, acc);
+                } else if (warp_rowmask) {
+                    pair_tile_lean<LN, EF, true>(M, sm, g, J, k - k0, nvalid,
+                                                 ncol, rsa, rca, rsu, rcu,
+                                                 acc);
                 } else {
-                    pair_tile<LN, EF, false>(M, sm, g, J, k - k0, false,
-                                             nvalid, TB, rsa, rca, rsu, rcu,
-                                             acc);
+                    pair_tile_lean<LN, EF, false>(M, sm, g, J, k - k0, nvalid,
+                                                  ncol, rsa, rca, rsu, rcu,
+                                                  acc);
                 }
             }
         }
