@@ -2310,7 +2310,9 @@ static int vmc_run_block_impl(qmcb_handle *h, int64_t ns, double *lnpsi,
     a.out_confs = confs ? reinterpret_cast<double *>(scr + off_cf) : nullptr;
     a.accept_rate = h->vmc_acc;
     a.sum_energy = h->vmc_sum_e;
-    a.sum_ssf = (M && sum_ssf) ? h->vmc_sum_ssf : nullptr;
+    // the block sums of S(k) are always accumulated on the device (that is
+    // the estimator); `sum_ssf` only says whether they are shipped
+    a.sum_ssf = M ? h->vmc_sum_ssf : nullptr;
     if (a.sum_ssf)
         CUDA_TRY(h, cudaMemsetAsync(h->vmc_sum_ssf, 0,
                                     C * M * 3 * sizeof(double), h->stream));
