@@ -1554,7 +1554,7 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
         // rows of pure S(k), the bin lists of the density): every
         // `rebalance_every` steps look at the counts of all ranks (one
         // 8 (R + 1)-byte read) and even the slabs out when they have drifted
-        // apart by more than 2 %, or when one of them nears its capacity
+        // apart by more than 1 %, or when one of them nears its capacity
         // (the reference truncates at the GLOBAL capacity only).
         if (h->comm && !do_den && (!do_ssf || !h->dp.ssf_as_pure)
             && h->rebalance_every > 0
@@ -1569,7 +1569,7 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
                 mx = std::max(mx, offs[q + 1] - offs[q]);
                 mn = std::min(mn, offs[q + 1] - offs[q]);
             }
-            if (mx - mn > 1 && ((double) mx > 1.02 * (double) mn
+            if (mx - mn > 1 && ((double) mx > 1.01 * (double) mn
                                 || (double) mx > 0.9 * (double) B.cap)) {
                 int64_t mv = 0;
                 rc = qmcb_dmc_rebalance(h, &mv);
