@@ -330,6 +330,13 @@ QMCB_API int qmcb_vmc_run_chain(qmcb_handle *h, int64_t ns, double *lnpsi,
                                 double *energy, uint8_t *move_stat,
                                 double *confs, double *accept_rate);
 
+/* One-body density matrix estimator g1(s) of the CURRENT state of every chain
+ * at the displacements `offsets` (reference hook `CoreFuncs.one_body_density`,
+ * qmc_base/jastrow/vmc.py:267-301, over `ith_one_body_density`
+ * jastrow/model.py:859-965), evaluated where the chains live: out [C][S]. */
+QMCB_API int qmcb_vmc_one_body_density(qmcb_handle *h, const double *offsets,
+                                       int32_t num_offsets, double *out);
+
 /* Current configurations [C][2][N] and ln|Psi| [C] (last_state). */
 QMCB_API int qmcb_vmc_get_state(qmcb_handle *h, double *confs, double *lnpsi);
 

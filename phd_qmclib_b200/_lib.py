@@ -25,7 +25,7 @@ SYMBOLS = [
     'qmcb_one_body_density', 'qmcb_one_body_density_device',
     'qmcb_fourier_density_k', 'qmcb_set_model_params', 'qmcb_cs_load',
     'qmcb_cs_variance', 'qmcb_dmc_reblock_reset', 'qmcb_dmc_reblock_get',
-    'qmcb_vmc_run_chain',
+    'qmcb_vmc_run_chain', 'qmcb_vmc_one_body_density',
 ]
 
 
@@ -128,6 +128,7 @@ def load():
     L.qmcb_vmc_init.argtypes = [vp, C.POINTER(VMCParams), vp, i64]
     L.qmcb_vmc_run_block.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp]
     L.qmcb_vmc_run_chain.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    L.qmcb_vmc_one_body_density.argtypes = [vp, vp, i32, vp]
     L.qmcb_vmc_get_state.argtypes = [vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)

@@ -2258,6 +2258,30 @@ int qmcb_vmc_run_block(qmcb_handle *h, int64_t ns, double *lnpsi,
                               accept_rate, sum_energy, sum_ssf, nullptr);
 }
 
+int qmcb_vmc_one_body_density(qmcb_handle *h, const double *offsets,
+                              int32_t num_offsets, double *out)
+{
+    if (!h) return QMCB_ERR_INVALID;
+    if (!h->vmc_ready) FAIL(h, QMCB_ERR_STATE, "qmcb_vmc_init not called");
+    if (num_offsets < 0 || (num_offsets > 0 && (!offsets || !out)))
+        FAIL(h, QMCB_ERR_INVALID, "bad arguments");
+    if (num_offsets == 0) return QMCB_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t C = (size_t) h->vmc_chains, S = (size_t) num_offsets;
+    int rc = ensure_scratch(h, (S + C * S) * sizeof(double));
+    if (rc) return rc;
+    double *d_off = h->d_scratch, *d_out = d_off + S;
+    CUDA_TRY(h, cudaMemcpyAsync(d_off, offsets, S * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+    rc = qmcb_one_body_density_device(h, h->V.confs, h->vmc_chains, d_off,
+                                      num_offsets, d_out);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(out, d_out, C * S * sizeof(double),
+                                cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return QMCB_OK;
+}
+
 int qmcb_vmc_run_chain(qmcb_handle *h, int64_t ns, double *lnpsi,
                        double *energy, uint8_t *move_stat, double *confs,
                        double *accept_rate)

@@ -483,6 +483,16 @@ class Engine:
         self._check(rc, 'qmcb_vmc_run_chain')
         return out
 
+    def vmc_one_body_density(self, offsets):
+        """g1 of the current state of every chain at ``offsets`` (S,) ->
+        (C, S), evaluated on the device."""
+        offsets = _f64(np.atleast_1d(offsets))
+        out = np.empty((self._vmc_chains, offsets.shape[0]))
+        rc = self._L.qmcb_vmc_one_body_density(
+            self._h, ptr(offsets), offsets.shape[0], ptr(out))
+        self._check(rc, 'qmcb_vmc_one_body_density')
+        return out
+
     def vmc_get_state(self):
         c = self._vmc_chains
         confs, ln = np.empty((c, 2, self.nop)), np.empty(c)

@@ -265,6 +265,24 @@ class Sampling:
         while True:
             yield self.engine.vmc_run_block(ns, series=False, sums=True)
 
+    def one_body_density_blocks(self, num_steps_block: int, ini_state: State,
+                                pos_offset) -> t.Iterator[np.ndarray]:
+        """The one-body density matrix estimator g1(s) along the chains
+        (the reference's VMC hook ``one_body_density(step_idx, pos_offset,
+        sys_conf, cfc_spec, iter_obd_array)``, qmc_base/jastrow/vmc.py:267-301,
+        which its own ``blocks()`` never reaches for this model): after every
+        block of ``num_steps_block`` steps, g1 of the state each chain is in,
+        at the displacements ``pos_offset`` -> array (chains, len(pos_offset))
+        (one row for a single chain).  Evaluated on the device where the
+        chains live."""
+        ns = int(num_steps_block)
+        single = self._start(ini_state)
+        pos_offset = np.atleast_1d(np.asarray(pos_offset, dtype=np.float64))
+        while True:
+            self.engine.vmc_run_block(ns, series=False)
+            obd = self.engine.vmc_one_body_density(pos_offset)
+            yield obd[0] if single else obd
+
     def states(self, ini_state: State) -> t.Iterator[State]:
         """One State per Metropolis step (reference qmc_base/vmc.py:244-253).
         """

@@ -336,6 +336,47 @@ def test_vmc_batched_chains_seed_dmc():
     assert 200 < blk.iter_props.num_walkers[-1] <= 320
 
 
+def test_vmc_chain_recording_and_obd_hook(oracle):
+    """`as_chain` / `state_data_blocks` record every state of a batch of
+    chains in ONE launch (qmcb_vmc_run_chain): the recorded states must be
+    the states `blocks()` walks for the same seed, a rejected step repeats
+    the previous state, and the one-body density matrix hook
+    (qmc_base/jastrow/vmc.py:267-301) evaluated where the chains live equals
+    the oracle's g1 of those states."""
+    from phd_qmclib_b200 import model, vmc
+    spec = model.Spec(**SPECS['frac_n21'])
+    p = model.param_block(spec)
+    nch, ns = 37, 24
+    ini_confs = _ini(spec, nch, 3)
+    a = vmc.Sampling(spec, 0.3, rng_seed=4)
+    chain = a.as_chain(ns, a.build_state(ini_confs))
+    assert chain.confs.shape == (nch, ns, 2, spec.boson_number)
+    b = vmc.Sampling(spec, 0.3, rng_seed=4)
+    blk = next(b.blocks(ns, b.build_state(ini_confs)))
+    assert np.array_equal(chain.props.move_stat, blk.iter_props.move_stat)
+    assert np.array_equal(chain.props.wf_abs_log, blk.iter_props.wf_abs_log)
+    assert np.array_equal(chain.props.energy, blk.iter_props.energy)
+    assert np.array_equal(chain.confs[:, -1], blk.last_state.sys_conf)
+    assert np.array_equal(chain.confs[:, 0, 0], ini_confs[:, 0])
+    rej = ~chain.props.move_stat[:, 1:]
+    same = np.all(chain.confs[:, 1:, 0] == chain.confs[:, :-1, 0], axis=-1)
+    assert rej.any() and np.all(same[rej]) and not np.any(same[~rej])
+    # ln|Psi| of the recorded states against the oracle
+    ln = oracle.model_eval(p, chain.confs[:, 7], want=('lnpsi',))['lnpsi']
+    assert np.max(np.abs(ln - chain.props.wf_abs_log[:, 7])) < 1e-11
+    a.engine.close()
+    b.engine.close()
+    c = vmc.Sampling(spec, 0.3, rng_seed=4)
+    offs = np.linspace(0.0, 0.5 * spec.supercell_size, 9)
+    it = c.one_body_density_blocks(ns, c.build_state(ini_confs), offs)
+    g1 = next(it)
+    assert g1.shape == (nch, 9)
+    want = oracle.one_body_density(p, chain.confs[:, -1], offs)
+    assert np.max(np.abs(g1 - want) / np.abs(want)) < 1e-11
+    assert np.all(g1[:, 0] == 1.0)
+    c.engine.close()
+
+
 def test_state_data_blocks():
     """Reference tests/mrbp_qmc/test_dmc.py:118-136 / test_vmc.py: blocks
     that keep every state."""
