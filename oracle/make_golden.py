@@ -394,6 +394,61 @@ def gen_dmc_stat(mrbp, name, kwargs, *, n_target, wmax, dt, nts, nblocks,
           f' <|rho_k|^2>/N = {sk_mean / nop}')
 
 
+def gen_dmc_stat_pure(mrbp, name, kwargs, *, n_target, wmax, dt, nts, nblocks,
+                      burn, seed, nwc=0.5, num_modes=8, num_bins=50,
+                      parallel=True):
+    """A reference DMC run at a BASELINE particle number with the PURE
+    (forward-walking) S(k) and density estimators, reduced per block the way
+    qmc_exec/dmc/proc.py:304-350 does it (pure estimators: the entry of the
+    last step of a block, weighted by that step's population; energies: block
+    sums), starting from the lattice configuration of bench.py.  Default
+    `jit_parallel=True`, the mode Proc.sampling always runs."""
+    model, dmc = mrbp.model, mrbp.dmc
+    spec = model.Spec(**kwargs)
+    nop = spec.boson_number
+    ssf_spec = dmc.SSFEstSpec(num_modes, as_pure_est=True,
+                              pfw_num_time_steps=nts)
+    den_spec = dmc.DensityEstSpec(num_bins, as_pure_est=True,
+                                  pfw_num_time_steps=nts)
+    sampling = dmc.Sampling(spec, dt, wmax, n_target,
+                            num_walkers_control_factor=nwc, rng_seed=seed,
+                            ssf_est_spec=ssf_spec, density_est_spec=den_spec,
+                            jit_parallel=parallel)
+    rng = np.random.default_rng(seed)
+    confs = np.zeros((n_target, 2, nop))
+    confs[:, 0, :] = (np.arange(nop)[None, :] + 0.25
+                      + 0.15 * (rng.random((n_target, nop)) - 0.5))
+    ini_state = sampling.build_state(confs)
+    e_sum, w_sum, s_last, d_last, n_last = [], [], [], [], []
+    for b, block in zip(range(burn + nblocks),
+                        sampling.blocks(ini_state, nts, burn)):
+        if b < burn:
+            continue
+        e_sum.append(block.iter_props.energy.sum())
+        w_sum.append(block.iter_props.weight.sum())
+        s_last.append(np.asarray(block.iter_ssf)[nts - 1].copy())
+        d_last.append(np.asarray(block.iter_density)[nts - 1, :, 0].copy())
+        n_last.append(float(block.iter_props.num_walkers[nts - 1]))
+    e_sum, w_sum = np.array(e_sum), np.array(w_sum)
+    s_last, d_last = np.array(s_last), np.array(d_last)
+    n_last = np.array(n_last)
+    e_mean = e_sum.sum() / w_sum.sum()
+    _, e_err = _ref_reblock((e_sum - e_mean * w_sum) / w_sum.mean())
+    out = dict(params=param_block(spec), ini_confs=confs, n_target=n_target,
+               max_num_walkers=wmax, time_step=dt, nts=nts, nblocks=nblocks,
+               burn=burn, nwc_factor=nwc, num_modes=num_modes,
+               num_bins=num_bins, block_energy=e_sum, block_weight=w_sum,
+               block_ssf_last=s_last, block_density_last=d_last,
+               block_walkers_last=n_last, ref_energy_mean=e_mean,
+               ref_energy_err=e_err, parallel=int(parallel))
+    np.savez_compressed(os.path.join(GOLDEN, f'dmc_stat_pure_{name}.npz'),
+                        **out)
+    sk = s_last[:, :, 0].sum(axis=0) / n_last.sum() / nop
+    print(f'dmc_stat_pure_{name}: E/N = {e_mean / nop:.6f} +- '
+          f'{e_err / nop:.6f}; pure <|rho_k|^2>/N = {sk}; '
+          f'density per bin = {d_last.sum(axis=0)[:4] / n_last.sum()}')
+
+
 def gen_vmc_stat(mrbp, name, kwargs, *, move_spread, ns, nblocks, burn, seed,
                  num_modes=8):
     """A long single-chain reference VMC run (qmc_base/vmc.py:557-770):
@@ -555,6 +610,11 @@ def main():
                        np.random.default_rng(502), draw_uniform,
                        move_spread=math.sqrt(2e-3), ns=24, nblocks=2,
                        num_modes=10, seed=7, gaussian=True)
+    if 'statpure' in which:
+        # BASELINE configs[2] model (N=50), 512 walkers, pure estimators
+        gen_dmc_stat_pure(mrbp, 'lat_n50', SPECS['lat_n50'], n_target=512,
+                          wmax=640, dt=1e-3, nts=64, nblocks=64, burn=16,
+                          seed=21)
     if 'stat' in which:
         gen_dmc_stat(mrbp, 'll_n16', SPECS['ll_n16'], n_target=512, wmax=640,
                      dt=2e-3, nts=256, nblocks=48, burn=12, seed=11)

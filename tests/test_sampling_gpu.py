@@ -377,6 +377,79 @@ def test_vmc_chain_recording_and_obd_hook(oracle):
     c.engine.close()
 
 
+def test_dmc_pure_estimators_n50_vs_reference_run():
+    """Statistical parity at a BASELINE particle number (configs[2] model,
+    N=50) for the PURE (forward-walking) S(k) and density estimators and the
+    energy: the engine against a frozen run of the live reference
+    (oracle/make_golden.py: gen_dmc_stat_pure, `jit_parallel=True` like
+    Proc.sampling), reduced per block as qmc_exec/dmc/proc.py:304-350 does
+    (last step of a block, weighted by that step's population)."""
+    from phd_qmclib_b200 import dmc
+    g = golden('dmc_stat_pure_lat_n50.npz')
+    p = g['params']
+    nop = int(p[3])
+    nts, nblocks, burn = int(g['nts']), int(g['nblocks']), int(g['burn'])
+    M, B = int(g['num_modes']), int(g['num_bins'])
+
+    class _Spec:
+        params, obf_params, tbf_params = p[:12], p[12:19], p[19:]
+        boson_number, supercell_size = nop, float(p[4])
+        boundaries = (0.0, float(p[4]))
+        sys_conf_shape = (2, nop)
+
+    smp = dmc.Sampling(_Spec, float(g['time_step']),
+                       int(g['max_num_walkers']), int(g['n_target']),
+                       num_walkers_control_factor=float(g['nwc_factor']),
+                       rng_seed=99,
+                       ssf_est_spec=dmc.SSFEstSpec(M, True, nts),
+                       density_est_spec=dmc.DensityEstSpec(B, True, nts))
+    it = smp.blocks(smp.build_state(g['ini_confs']), nts, burn)
+    for _ in islice(it, burn):
+        pass
+    e_sum, w_sum, s_last, d_last, n_last = [], [], [], [], []
+    for _, blk in zip(range(4 * nblocks), it):
+        e_sum.append(blk.iter_props.energy.sum())
+        w_sum.append(blk.iter_props.weight.sum())
+        s_last.append(np.asarray(blk.iter_ssf)[nts - 1, :, 0].copy())
+        d_last.append(np.asarray(blk.iter_density)[nts - 1, :, 0].copy())
+        n_last.append(float(blk.iter_props.num_walkers[nts - 1]))
+    smp.engine.close()
+    s_last, d_last, n_last = map(np.array, (s_last, d_last, n_last))
+    e_eng, err_eng = ratio_mean_error(e_sum, w_sum)
+    e_ref, err_ref = ratio_mean_error(g['block_energy'], g['block_weight'])
+    err_ref = max(err_ref, float(g['ref_energy_err']))
+    z = (e_eng - e_ref) / np.hypot(err_ref, err_eng)
+    print(f'dmc pure N=50 E/N: {e_eng / nop:.5f} vs {e_ref / nop:.5f}, '
+          f'z = {z:+.2f}')
+    assert abs(z) < 4
+    rs, rn = g['block_ssf_last'][:, :, 0], g['block_walkers_last']
+    zs = []
+    for m in range(M):
+        a, da = ratio_mean_error(s_last[:, m], n_last)
+        b, db = ratio_mean_error(rs[:, m], rn)
+        if m == 0:
+            assert a == pytest.approx(nop ** 2, rel=1e-12)
+            assert b == pytest.approx(nop ** 2, rel=1e-12)
+            continue
+        zs.append((a - b) / np.hypot(da, db))
+    print('pure S(k) z:', np.round(zs, 2))
+    assert np.max(np.abs(zs)) < 4.5
+    rd = g['block_density_last']
+    zd = []
+    for b_ in range(B):
+        a, da = ratio_mean_error(d_last[:, b_], n_last)
+        b, db = ratio_mean_error(rd[:, b_], rn)
+        zd.append((a - b) / np.hypot(da, db))
+    zd = np.array(zd)
+    print(f'pure density z: max {np.abs(zd).max():.2f} rms '
+          f'{np.sqrt(np.mean(zd ** 2)):.2f}')
+    # 50 bins: the largest of 50 normal deviates stays below 4.5, their rms
+    # near 1
+    assert np.abs(zd).max() < 4.5 and np.sqrt(np.mean(zd ** 2)) < 1.6
+    # each walker contributes N counts
+    assert np.allclose(d_last.sum(axis=1) / n_last, nop, rtol=0.05)
+
+
 def test_state_data_blocks():
     """Reference tests/mrbp_qmc/test_dmc.py:118-136 / test_vmc.py: blocks
     that keep every state."""
