@@ -612,8 +612,10 @@ def main():
                        num_modes=10, seed=7, gaussian=True)
     if 'statpure' in which:
         # BASELINE configs[2] model (N=50), 512 walkers, pure estimators
+        # (tau = 20 after a burn-in of tau = 3: long against the relaxation
+        # of the slowest S(k) mode, so that the blocked errors are honest)
         gen_dmc_stat_pure(mrbp, 'lat_n50', SPECS['lat_n50'], n_target=512,
-                          wmax=640, dt=1e-3, nts=64, nblocks=64, burn=16,
+                          wmax=640, dt=1e-3, nts=128, nblocks=160, burn=24,
                           seed=21)
     if 'stat' in which:
         gen_dmc_stat(mrbp, 'll_n16', SPECS['ll_n16'], n_target=512, wmax=640,
