@@ -293,79 +293,75 @@ def cpu_port_units_per_s(cfg, budget_s=12.0, threads=None):
                        f'oracle/qmc_oracle.c with OpenMP')
 
 
-def cpu_reference_units_per_s(cfg, budget_s=20.0, serial_too=False,
-                              max_blocks=6):
+def reference_runner(cfg, parallel=True, shrink=1):
     """The LIVE reference under oracle/refshim.py (protocol of SURVEY.md 8d /
-    BASELINE.md section 3).  Raises RuntimeError with the reason when the
-    reference cannot run here."""
+    BASELINE.md section 3) as an object whose `step()` times one more block.
+    Raises RuntimeError with the reason when it cannot run here."""
     _oracle_path()
     import ref_arm
     ok, why = ref_arm.probe()
     if not ok:
         raise RuntimeError(why)
-    n = cfg['nop']
     kw = spec_kwargs(cfg)
     if cfg['kind'] == 'vmc':
         from phd_qmclib_b200 import model
-        r = ref_arm.vmc_chain_steps_per_s(
+        return ref_arm.VmcRun(
             kw, move_spread=0.25 * model.Spec(**kw).well_width,
-            ns=cfg['ref']['ns'], num_modes=cfg['modes'], budget_s=budget_s,
-            max_blocks=max_blocks)
-    else:
-        nw = cfg['ref']['nw']
-        common = dict(nw=nw, cap=int(nw * CAP_FACTOR), dt=cfg['dt'], nwc=NWC,
-                      nts=cfg['ref']['nts'], num_modes=cfg['modes'],
-                      num_bins=cfg['bins'], max_blocks=max_blocks)
-        r = ref_arm.dmc_walker_steps_per_s(kw, parallel=True,
-                                           budget_s=budget_s, **common)
-        if serial_too:
-            common.update(nw=max(64, nw // 8), cap=int(max(64, nw // 8)
-                                                       * CAP_FACTOR))
-            s = ref_arm.dmc_walker_steps_per_s(kw, parallel=False,
-                                               budget_s=budget_s / 2,
-                                               **common)
-            r['serial'] = dict(value=s['value'], cores=1, sample=s['sample'])
-    r.update(unit=cfg['unit'], kind='reference', cpu_model=ref_arm.cpu_model(),
-             host_cores=os.cpu_count())
-    return r
+            ns=cfg['ref']['ns'], num_modes=cfg['modes'])
+    nw = max(64, cfg['ref']['nw'] // shrink)
+    return ref_arm.DmcRun(kw, nw=nw, cap=int(nw * CAP_FACTOR), dt=cfg['dt'],
+                          nwc=NWC, nts=cfg['ref']['nts'], parallel=parallel,
+                          num_modes=cfg['modes'], num_bins=cfg['bins'])
 
 
-def cpu_baseline(cfg, serial_too=False, budget_s=20.0, max_blocks=6):
-    """kind "reference" when the Numba reference runs here, else the port
-    with the reason it was used."""
-    try:
-        return cpu_reference_units_per_s(cfg, budget_s=budget_s,
-                                         serial_too=serial_too,
-                                         max_blocks=max_blocks)
-    except Exception as exc:       # noqa: BLE001 - any failure is a reason
-        r = cpu_port_units_per_s(cfg)
-        r['reason'] = ('reference (Numba) arm unavailable: '
-                       f'{exc.__class__.__name__}: {exc}'[:400])
-        return r
+class PortRunner:
+    """Fallback: the C port of oracle/ (kind "port"), with the reason."""
+
+    def __init__(self, cfg, reason):
+        self.cfg, self.reason = cfg, reason
+        self.sample, self.cores = '', os.cpu_count() or 1
+
+    def step(self):
+        r = cpu_port_units_per_s(self.cfg, budget_s=4.0)
+        self.sample, self.cores = r['sample'], r['cores']
+        return r['value'] * r['seconds'], r['seconds']
 
 
 def run_reference(name, cfg, args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
+    cb = {'unit': cfg['unit']}
+    try:
+        run = reference_runner(cfg)
+        _oracle_path()
+        import ref_arm
+        cb.update(kind='reference', threading_layer=run.layer,
+                  numba=run.numba, cpu_model=ref_arm.cpu_model(),
+                  host_cores=os.cpu_count(),
+                  jit_and_first_block_s=run.first_block_s)
+    except Exception as exc:       # noqa: BLE001 - any failure is a reason
+        run = PortRunner(cfg, 'reference (Numba) arm unavailable: '
+                         f'{exc.__class__.__name__}: {exc}'[:400])
+        cb.update(kind='port', reason=run.reason)
+    # each bench "step" is one block of the bounded sample; the JIT
+    # compilation of the reference (~1-2 min) happened in the constructor
     per_step = []
-    last = None
-    # each "step" is a bounded sample sized to keep the whole run short; the
-    # JIT compilation of the reference (~1-2 min) happens once, in step 0
-    total = max(1, args.steps + args.warmup)
-    budget = max(2.0, min(12.0, 90.0 / total))
-    for i in range(total):
-        r = cpu_baseline(cfg, serial_too=(i == total - 1), budget_s=budget,
-                         max_blocks=3)
-        if i >= args.warmup:
-            per_step.append((r['value'], r['seconds']))
-            last = r
-    value = float(np.mean([v for v, _ in per_step]))
-    ms = float(np.mean([d for _, d in per_step])) * 1e3
-    cb = {k: last[k] for k in ('unit', 'cores', 'kind', 'sample',
-                               'threading_layer', 'numba', 'cpu_model',
-                               'host_cores', 'serial', 'reason') if k in last}
-    cb['value'] = value
+    for i in range(max(1, args.steps + args.warmup)):
+        units, secs = run.step()
+        if i >= args.warmup or args.steps + args.warmup == 0:
+            per_step.append((units, secs))
+    value = float(sum(u for u, _ in per_step) / sum(t for _, t in per_step))
+    ms = float(np.mean([t for _, t in per_step])) * 1e3
+    cb.update(value=value, cores=run.cores, sample=run.sample)
+    if cb['kind'] == 'reference' and cfg['kind'] == 'dmc':
+        # one core, for the record (its own JIT compilation; smaller sample)
+        try:
+            ser = reference_runner(cfg, parallel=False, shrink=8)
+            u, t = ser.step()
+            cb['serial'] = {'value': u / t, 'cores': 1, 'sample': ser.sample}
+        except Exception as exc:    # noqa: BLE001
+            cb['serial'] = {'value': None, 'reason': str(exc)[:200]}
     line = {
         'impl': 'reference', 'metric': cfg['metric'],
         'value': value, 'unit': cfg['unit'], 'n_gpus': args.gpus,
@@ -387,7 +383,7 @@ def cpu_baseline_subprocess(name):
     process (its own OpenMP/Numba thread pools, none of torch's) and takes
     the cpu_baseline object of its line."""
     cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference',
-           '--config', name, '--steps', '1', '--warmup', '0']
+           '--config', name, '--steps', '2', '--warmup', '0']
     env = {k: v for k, v in os.environ.items()
            if k not in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE')}
     try:

@@ -43,90 +43,100 @@ def lattice_confs(nw, nop, seed):
     return ini
 
 
-def dmc_walker_steps_per_s(spec_kwargs, *, nw, cap, dt, nwc, nts, parallel,
-                           budget_s=20.0, max_blocks=6, seed=7,
-                           num_modes=0, num_bins=0):
-    """Run the reference's DMC ``blocks()``; returns a dict with the
-    throughput (walker-steps/s over the timed blocks), the thread count, the
-    Numba threading layer and a description of the sample."""
-    import numba
-    mrbp = _load()
-    model, dmc = mrbp.model, mrbp.dmc
-    spec = model.Spec(**spec_kwargs)
-    nop = spec.boson_number
-    kw = {}
-    if num_modes:
-        kw['ssf_est_spec'] = dmc.SSFEstSpec(num_modes, as_pure_est=True,
-                                            pfw_num_time_steps=nts)
-    if num_bins:
-        kw['density_est_spec'] = dmc.DensityEstSpec(num_bins,
-                                                    as_pure_est=True,
-                                                    pfw_num_time_steps=nts)
-    sampling = dmc.Sampling(spec, dt, cap, nw,
-                            num_walkers_control_factor=nwc, rng_seed=seed,
-                            jit_parallel=bool(parallel), **kw)
-    ini_state = sampling.build_state(lattice_confs(nw, nop, 11))
-    blocks = sampling.blocks(ini_state, nts, 0)
-    t0 = time.perf_counter()
-    next(blocks)                        # JIT compilation + first block
-    jit_s = time.perf_counter() - t0
-    ws, secs, nb = 0.0, 0.0, 0
-    while nb < max_blocks and (nb < 1 or secs < budget_s):
+class DmcRun:
+    """One reference DMC sampling kept alive: `step()` times one more block
+    of `Sampling.blocks()` (the JIT compilation and the first block happen
+    in the constructor and are not timed)."""
+
+    def __init__(self, spec_kwargs, *, nw, cap, dt, nwc, nts, parallel,
+                 seed=7, num_modes=0, num_bins=0):
+        import numba
+        mrbp = _load()
+        model, dmc = mrbp.model, mrbp.dmc
+        spec = model.Spec(**spec_kwargs)
+        nop = spec.boson_number
+        kw = {}
+        if num_modes:
+            kw['ssf_est_spec'] = dmc.SSFEstSpec(num_modes, as_pure_est=True,
+                                                pfw_num_time_steps=nts)
+        if num_bins:
+            kw['density_est_spec'] = dmc.DensityEstSpec(
+                num_bins, as_pure_est=True, pfw_num_time_steps=nts)
+        sampling = dmc.Sampling(spec, dt, cap, nw,
+                                num_walkers_control_factor=nwc, rng_seed=seed,
+                                jit_parallel=bool(parallel), **kw)
+        ini_state = sampling.build_state(lattice_confs(nw, nop, 11))
+        self.blocks = sampling.blocks(ini_state, nts, 0)
         t0 = time.perf_counter()
-        blk = next(blocks)
-        secs += time.perf_counter() - t0
-        ws += float(np.asarray(blk.iter_props.num_walkers, dtype=np.float64)
-                    .sum())
-        nb += 1
-    threads = numba.get_num_threads() if parallel else 1
-    layer = None
-    if parallel:
-        try:
-            layer = numba.threading_layer()
-        except Exception:       # no parallel region has run
-            layer = 'unknown'
-    return dict(value=ws / secs, cores=int(threads), threading_layer=layer,
-                blocks=nb, seconds=secs, first_block_s=jit_s,
-                numba=numba.__version__,
-                sample=(f'{nw} target / {cap} capacity walkers x {nts} time '
-                        f'steps x {nb} blocks (first block discarded: JIT), '
-                        f'mrbp_qmc.dmc.Sampling(jit_parallel={bool(parallel)})'
-                        f'.blocks() of the unmodified reference under '
-                        f'oracle/refshim.py, numba {numba.__version__}'))
+        next(self.blocks)                   # JIT compilation + first block
+        self.first_block_s = time.perf_counter() - t0
+        self.parallel = bool(parallel)
+        self.nsteps = 0
+        self.cores = int(numba.get_num_threads()) if parallel else 1
+        self.layer = None
+        if parallel:
+            try:
+                self.layer = numba.threading_layer()
+            except Exception:       # no parallel region has run
+                self.layer = 'unknown'
+        self.numba = numba.__version__
+        self._what = (f'{nw} target / {cap} capacity walkers x {nts} time '
+                      f'steps')
+        self._est = (f', pure S(k) M={num_modes} and density B={num_bins} '
+                     f'every step' if (num_modes or num_bins) else '')
+
+    def step(self):
+        """(units, seconds) of one more block."""
+        t0 = time.perf_counter()
+        blk = next(self.blocks)
+        secs = time.perf_counter() - t0
+        self.nsteps += 1
+        ws = float(np.asarray(blk.iter_props.num_walkers, dtype=np.float64)
+                   .sum())
+        return ws, secs
+
+    @property
+    def sample(self):
+        return (f'{self._what}{self._est} per bench step (first block '
+                f'discarded: JIT), mrbp_qmc.dmc.Sampling(jit_parallel='
+                f'{self.parallel}).blocks() of the unmodified reference '
+                f'under oracle/refshim.py, numba {self.numba}')
 
 
-def vmc_chain_steps_per_s(spec_kwargs, *, move_spread, ns, num_modes,
-                          budget_s=15.0, max_blocks=8, seed=1):
-    """Single Metropolis chain of the reference (``mrbp_qmc.vmc.Sampling``,
-    ``qmc_base/vmc.py:670-770``): chain-steps/s on one core."""
-    import numba
-    mrbp = _load()
-    model, vmc = mrbp.model, mrbp.vmc
-    spec = model.Spec(**spec_kwargs)
-    nop = spec.boson_number
-    kw = {}
-    if num_modes:
-        kw['ssf_est_spec'] = vmc.SSFEstSpec(num_modes)
-    sampling = vmc.Sampling(spec, move_spread, rng_seed=seed, **kw)
-    ini = lattice_confs(1, nop, 0)[0]
-    ini_state = sampling.build_state(ini)
-    blocks = sampling.blocks(ns, ini_state)
-    t0 = time.perf_counter()
-    next(blocks)
-    jit_s = time.perf_counter() - t0
-    secs, nb = 0.0, 0
-    while nb < max_blocks and (nb < 1 or secs < budget_s):
+class VmcRun:
+    """Single Metropolis chain of the reference (`mrbp_qmc.vmc.Sampling`,
+    `qmc_base/vmc.py:670-770`): one core by construction."""
+
+    def __init__(self, spec_kwargs, *, move_spread, ns, num_modes, seed=1):
+        import numba
+        mrbp = _load()
+        model, vmc = mrbp.model, mrbp.vmc
+        spec = model.Spec(**spec_kwargs)
+        kw = {}
+        if num_modes:
+            kw['ssf_est_spec'] = vmc.SSFEstSpec(num_modes)
+        sampling = vmc.Sampling(spec, move_spread, rng_seed=seed, **kw)
+        ini_state = sampling.build_state(
+            lattice_confs(1, spec.boson_number, 0)[0])
+        self.blocks = sampling.blocks(ns, ini_state)
         t0 = time.perf_counter()
-        next(blocks)
-        secs += time.perf_counter() - t0
-        nb += 1
-    return dict(value=ns * nb / secs, cores=1, threading_layer=None,
-                blocks=nb, seconds=secs, first_block_s=jit_s,
-                numba=numba.__version__,
-                sample=(f'one chain x {ns} steps x {nb} blocks (first block '
-                        f'discarded: JIT), mrbp_qmc.vmc.Sampling.blocks() of '
-                        f'the unmodified reference under oracle/refshim.py, '
-                        f'numba {numba.__version__}'))
+        next(self.blocks)
+        self.first_block_s = time.perf_counter() - t0
+        self.ns = ns
+        self.cores, self.layer, self.parallel = 1, None, False
+        self.numba = numba.__version__
+
+    def step(self):
+        t0 = time.perf_counter()
+        next(self.blocks)
+        return float(self.ns), time.perf_counter() - t0
+
+    @property
+    def sample(self):
+        return (f'one chain x {self.ns} steps per bench step (first block '
+                f'discarded: JIT), mrbp_qmc.vmc.Sampling.blocks() of the '
+                f'unmodified reference under oracle/refshim.py, numba '
+                f'{self.numba}')
 
 
 def cpu_model():
