@@ -441,9 +441,18 @@ class Dist:
         self.affinity = bind_to_gpu_numa_node(self.local) \
             if self.world > 1 else None
         self.dist = None
+        self.stdout_fd = None
         if self.world > 1:
             import torch.distributed as dist
             os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            # stdout carries exactly one JSON line.  NCCL writes its version
+            # banner (NCCL_DEBUG=VERSION, the setting of the GPU boxes) to
+            # file descriptor 1 from C: the environment is left alone, fd 1
+            # points at stderr for the duration of the run, and the line
+            # goes to the saved descriptor.
+            sys.stdout.flush()
+            self.stdout_fd = os.dup(1)
+            os.dup2(2, 1)
             dist.init_process_group(
                 'nccl', device_id=torch.device('cuda', self.local))
             self.dist = dist
@@ -473,6 +482,14 @@ class Dist:
         t[self.rank] = x
         self.dist.all_reduce(t)
         return [float(v) for v in t.tolist()]
+
+    def emit(self, line):
+        data = (json.dumps(line) + '\n').encode()
+        if self.stdout_fd is None:
+            sys.stdout.write(data.decode())
+            sys.stdout.flush()
+        else:
+            os.write(self.stdout_fd, data)
 
     def close(self):
         if self.dist is not None:
@@ -822,7 +839,7 @@ def run_b200(name, cfg, args):
         line['cpu_baseline'] = None
         if D.world == 1 and not args.no_cpu:
             line['cpu_baseline'] = cpu_baseline_subprocess(name)
-        print(json.dumps(line), flush=True)
+        D.emit(line)
     D.close()
     return 0
 
