@@ -329,7 +329,7 @@ bool step_fast_ok(const qmcb_handle *h)
 bool choose_geom(const DevModel &M, int max_smem, GroupGeom &g,
                  std::string &err)
 {
-    const int regs_per_thread = 128;
+    const int regs_per_thread = TB == 2 ? 80 : 128;
     const char *env_odd = getenv("QMCB_ODD_ROWS");
     const int nbp = (env_odd && atoi(env_odd)) ? M.nb : M.nb + (M.nb & 1);
     double best = -1.0;

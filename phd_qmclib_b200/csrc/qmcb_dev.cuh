@@ -34,7 +34,10 @@
 
 namespace qmcb {
 
-constexpr int TB = 4;                 // particles owned by one thread
+#ifndef QMCB_TB
+#define QMCB_TB 4
+#endif
+constexpr int TB = QMCB_TB;           // particles owned by one thread
 constexpr double LN2 = 0.693147180559945309417232121458;
 
 // Node tables of the per-particle transcendentals (built once per model on
@@ -501,7 +504,7 @@ __device__ __forceinline__ void particle_tables(const DevModel &M, double z,
 // column-sum rows.  (A second, pre-scaled copy of the far table would save
 // one multiply per pair but costs more in shared-memory traffic and in
 // column-sum slots than it gains: measured -4 %.)
-constexpr int TAB_ROWS = 40;
+constexpr int TAB_ROWS = 10 * TB;
 constexpr int RED_ROWS = 0;
 
 struct GroupSmem {
@@ -521,12 +524,12 @@ struct GroupSmem {
     }
     __device__ __forceinline__ double2 *var(int g, int v, int c) const
     {
-        return reinterpret_cast<double2 *>(tab(g) + (TAB_ROWS - 32) * nbp)
-               + (v * 4 + c) * nbp;
+        return reinterpret_cast<double2 *>(tab(g) + 2 * TB * nbp)
+               + (v * TB + c) * nbp;
     }
     __device__ __forceinline__ double *q(int g, int k, int c) const
     {
-        return qreg(g) + (k * 4 + c) * nbp;
+        return qreg(g) + (k * TB + c) * nbp;
     }
     __device__ __forceinline__ double *red(int g, int which) const
     {
@@ -547,7 +550,7 @@ __host__ __device__ inline int group_q_stride(int nbp, int nb, int kc, int G,
 {
     // 8-byte elements, modulo 16 slots
     int want = interleave ? mod_inverse(G % 16, 16) : nb % 16;
-    return bank_stride((4 * kc + RED_ROWS) * nbp, want, 16);
+    return bank_stride((TB * kc + RED_ROWS) * nbp, want, 16);
 }
 
 __host__ __device__ inline int group_smem_doubles(int G, int nbp, int nb,
@@ -585,7 +588,7 @@ __device__ __forceinline__ void pair_tile(
 {
     const int nbp = sm.nbp;
     const int cstride = nbp * (int) sizeof(double2);    // next column particle
-    const unsigned vstride = 4u * (unsigned) cstride;   // next variant
+    const unsigned vstride = (unsigned) TB * (unsigned) cstride;   // next variant
     const char *pa1 = reinterpret_cast<const char *>(sm.a1(g, 0) + J);
     const char *pv = reinterpret_cast<const char *>(sm.var(g, 0, 0) + J);
     double *pq = sm.q(g, qslot, 0) + J;
@@ -670,7 +673,7 @@ __device__ __forceinline__ void pair_diag(
     const double (&rsa)[TB], const double (&rca)[TB],
     const double (&rsu)[TB], const double (&rcu)[TB], PairAcc &acc)
 {
-    const unsigned vstride = 4u * (unsigned) sm.nbp * (unsigned) sizeof(double2);
+    const unsigned vstride = (unsigned) TB * (unsigned) sm.nbp * (unsigned) sizeof(double2);
     const double s_m = M.s_m_scaled, mu = M.mu;
 #pragma unroll
     for (int c2 = 1; c2 < TB; ++c2) {
@@ -722,7 +725,7 @@ __device__ __forceinline__ void pair_tile_lean(
 {
     const int nbp = sm.nbp;
     const int cstride = nbp * (int) sizeof(double2);    // next column particle
-    const unsigned vstride = 4u * (unsigned) cstride;   // next variant
+    const unsigned vstride = (unsigned) TB * (unsigned) cstride;   // next variant
     const char *pa1 = reinterpret_cast<const char *>(sm.a1(g, 0) + J);
     const char *pv = reinterpret_cast<const char *>(sm.var(g, 0, 0) + J);
     double *pq = sm.q(g, qslot, 0) + J;
@@ -872,7 +875,7 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
     }
     __syncthreads();
 
-    double Tq[TB] = {0., 0., 0., 0.};   // column sums received from others
+    double Tq[TB] = {};   // column sums received from others
     const bool pairs = active && !M.is_ideal;
     const bool even = (nb & 1) == 0;
     // drift / energy kernels: the diagonal tile adds both ends of its pairs
@@ -941,7 +944,7 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
     if (!EF) __syncthreads();
 
     double epart = 0.0, lpart = 0.0;
-    double F[TB] = {0., 0., 0., 0.};
+    double F[TB] = {};
     if (active) {
         if (EF) {
             double f2 = 0.0;

@@ -48,8 +48,11 @@ __device__ __forceinline__ void load4(const double *row, int I, int nvalid,
 {
     if (vec_ok && nvalid == TB) {
         const double2 *p = reinterpret_cast<const double2 *>(row + TB * I);
-        double2 a = p[0], b = p[1];
-        x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+#pragma unroll
+        for (int c = 0; c < TB; c += 2) {
+            const double2 a = p[c / 2];
+            x[c] = a.x; x[c + 1] = a.y;
+        }
     } else {
 #pragma unroll
         for (int c = 0; c < TB; ++c)
@@ -62,8 +65,8 @@ __device__ __forceinline__ void store4(double *row, int I, int nvalid,
 {
     if (vec_ok && nvalid == TB) {
         double2 *p = reinterpret_cast<double2 *>(row + TB * I);
-        p[0] = make_double2(x[0], x[1]);
-        p[1] = make_double2(x[2], x[3]);
+#pragma unroll
+        for (int c = 0; c < TB; c += 2) p[c / 2] = make_double2(x[c], x[c + 1]);
     } else {
 #pragma unroll
         for (int c = 0; c < TB; ++c)
@@ -101,7 +104,7 @@ model_eval_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
         long long b = base + x.g;
         bool active = x.in_group && b < a.nconf;
         int nvalid = min(TB, N - TB * x.I);
-        double z[TB] = {0., 0., 0., 0.};
+        double z[TB] = {};
         if (active) {
             load4(a.confs + b * 2 * N, x.I, nvalid, vec_ok, z);
             if (a.state_confs)
@@ -502,7 +505,7 @@ __global__ void dmc_finalize_kernel(DmcBufs B, DmcConsts C, DmcLog L)
 #define QMCB_STEP_THREADS 256
 #endif
 #ifndef QMCB_STEP_MINCTAS
-#define QMCB_STEP_MINCTAS 2
+#define QMCB_STEP_MINCTAS (QMCB_TB == 2 ? 3 : 2)
 #endif
 // FAST: the per-particle transcendentals come from the model's node tables
 // (TrigTab); needs positions in [0, L], i.e. the recast interval of the
@@ -534,7 +537,7 @@ dmc_step_kernel(const __grid_constant__ DevModel M, GroupGeom geom, DmcBufs B,
     const bool active = x.in_group && s < W;
     const int nvalid = min(TB, N - TB * x.I);
 
-    double z[TB] = {0., 0., 0., 0.};
+    double z[TB] = {};
     int r = 0;
     if (active) {
         r = B.ref[s];
@@ -552,9 +555,16 @@ dmc_step_kernel(const __grid_constant__ DevModel M, GroupGeom geom, DmcBufs B,
                && B.ref[s - clone - 1] == r)
             ++clone;
         const uint32_t gp = (uint32_t) (ctl->pos_base[par] + r);
-        rng_normal4<FAST>(M.tt, C.seed, gp,
-                          (uint32_t) x.I | ((uint32_t) clone << 16),
-                          (uint32_t) t, STREAM_DIFFUSE, nrm);
+        {
+            // one Philox call serves the four particles of a 4-block
+            double n4[4];
+            const int q4 = (TB * x.I) / 4, o4 = (TB * x.I) % 4;
+            rng_normal4<FAST>(M.tt, C.seed, gp,
+                              (uint32_t) q4 | ((uint32_t) clone << 16),
+                              (uint32_t) t, STREAM_DIFFUSE, n4);
+#pragma unroll
+            for (int c = 0; c < TB; ++c) nrm[c] = n4[(o4 + c) & 3];
+        }
 #pragma unroll
         for (int c = 0; c < TB; ++c) {
             double zn = zp[c] + 2.0 * fp[c] * C.dt + C.sigma * nrm[c];

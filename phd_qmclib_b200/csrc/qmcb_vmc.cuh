@@ -59,7 +59,7 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
          base += (long long) gridDim.x * geom.G) {
         const long long c = base + x.g;
         const bool active = x.in_group && c < a.nchains;
-        double z[TB] = {0., 0., 0., 0.}, Fcur[TB] = {0., 0., 0., 0.};
+        double z[TB] = {}, Fcur[TB] = {};
         double ln_cur = 0.0, e_prev = 0.0, se = 0.0, se2 = 0.0;
         long long nacc = 0;
         if (active) {
@@ -81,15 +81,28 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
             if (active && !ini) {
                 double u[TB];
                 if (a.proposal == 1) {
-                    rng_normal4<FAST>(M.tt, a.seed, gc, (uint32_t) x.I,
-                                       (uint32_t) gs, STREAM_VMC_MOVE, u);
+                    {
+                        double n4[4];
+                        rng_normal4<FAST>(M.tt, a.seed, gc,
+                                          (uint32_t) ((TB * x.I) / 4),
+                                          (uint32_t) gs, STREAM_VMC_MOVE, n4);
+#pragma unroll
+                        for (int q = 0; q < TB; ++q)
+                            u[q] = n4[((TB * x.I) % 4 + q) & 3];
+                    }
 #pragma unroll
                     for (int q = 0; q < TB; ++q)
                         zp[q] = recast(z[q] + a.spread * u[q], a.z_min,
                                        a.size);
                 } else {
-                    rng_uniform4(a.seed, gc, (uint32_t) x.I, (uint32_t) gs,
-                                 STREAM_VMC_MOVE, u);
+                    {
+                        double u4[4];
+                        rng_uniform4(a.seed, gc, (uint32_t) ((TB * x.I) / 4),
+                                     (uint32_t) gs, STREAM_VMC_MOVE, u4);
+#pragma unroll
+                        for (int q = 0; q < TB; ++q)
+                            u[q] = u4[((TB * x.I) % 4 + q) & 3];
+                    }
 #pragma unroll
                     for (int q = 0; q < TB; ++q)
                         zp[q] = recast(z[q] + (u[q] - 0.5) * a.spread,

@@ -212,3 +212,58 @@ def test_branching_table_matches_serial_prefix_at_scale(oracle):
     want_e = float(ev['energy'][ref[:nw]].sum())
     assert abs(b['energy'][0] - want_e) < 1e-11 * abs(want_e)
     eng.close()
+
+
+def _vmc_vs_oracle(oracle, spec_kwargs, nch, ns, nblocks, modes, seed):
+    from phd_qmclib_b200 import engine, model
+    spec = model.Spec(**spec_kwargs)
+    p = model.param_block(spec)
+    nop, size = spec.boson_number, float(spec.supercell_size)
+    spread = 0.25 * spec.well_width
+    ini = _ini(np.random.default_rng(seed), nch, nop, size)
+    cur = ini.copy()
+    ln = oracle.model_eval(p, cur, want=('lnpsi',))['lnpsi']
+    eprev, sprev = np.zeros(nch), np.zeros((nch, modes, 3))
+    eng = engine.Engine(spec)
+    eng.vmc_init(ini, spread, seed, 0.0, size, ssf_num_modes=modes)
+    step0 = 0
+    for b in range(nblocks):
+        first = b == 0
+        a = oracle.vmc_block(p, seed, spread, 0.0, size, cur, ln, eprev,
+                             sprev, modes, ns, step0, first)
+        step0 += ns - (1 if first else 0)
+        o = eng.vmc_run_block(ns, series=True, sums=True)
+        assert np.array_equal(o['move_stat'], a['stat'])
+        assert np.max(np.abs(o['lnpsi'] - a['lnpsi'])
+                      / np.maximum(np.abs(a['lnpsi']), 1.0)) < 1e-11
+        assert np.max(np.abs(o['energy'] - a['energy'])
+                      / np.maximum(np.abs(a['energy']), 1.0)) < 1e-11
+        assert np.max(np.abs(o['ssf'] - a['ssf'])) < 1e-9
+        assert np.allclose(o['sum_ssf'], a['ssf'].sum(axis=1), rtol=1e-9,
+                           atol=1e-7)
+    confs, lnpsi = eng.vmc_get_state()
+    assert np.allclose(confs[:, 0], cur[:, 0], rtol=0, atol=1e-12)
+    eng.close()
+    return a
+
+
+def test_vmc_config1_n20_single_chain_vs_oracle(oracle):
+    """BASELINE configs[0] (the reference's own CPU case): N = 20 bosons,
+    V0 = 5 E_R, g = 4, one Metropolis chain, move spread a quarter of the
+    well, M = 20 modes (tests/mrbp_qmc/test_vmc_exec_proc.py:8-26): 3 blocks
+    of 2048 steps, accept/reject sequence identical to the oracle's."""
+    a = _vmc_vs_oracle(oracle, dict(
+        lattice_depth=5 * np.pi ** 2, lattice_ratio=1, interaction_strength=4,
+        boson_number=20, supercell_size=20, tbf_contact_cutoff=5), 1, 2048, 3,
+        20, 1)
+    assert 0.2 < a['accept_rate'][0] < 0.95
+
+
+def test_vmc_config2_n50_chains_vs_oracle(oracle):
+    """BASELINE configs[1] shape: N = 50 (a ragged last particle block), a
+    batch of chains with energy and S(k) M = 50, table path of the block
+    kernel."""
+    _vmc_vs_oracle(oracle, dict(
+        lattice_depth=5 * np.pi ** 2, lattice_ratio=1, interaction_strength=4,
+        boson_number=50, supercell_size=50, tbf_contact_cutoff=12.5), 1500,
+        24, 2, 50, 3)
