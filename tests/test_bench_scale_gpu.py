@@ -267,3 +267,48 @@ def test_vmc_config2_n50_chains_vs_oracle(oracle):
         lattice_depth=5 * np.pi ** 2, lattice_ratio=1, interaction_strength=4,
         boson_number=50, supercell_size=50, tbf_contact_cutoff=12.5), 1500,
         24, 2, 50, 3)
+
+
+@pytest.mark.parametrize('energy_mode', [0, 1])
+def test_sharded_code_path_on_one_rank_vs_oracle(oracle, energy_mode):
+    """The multi-rank machinery on a communicator of ONE rank (what a
+    single-GPU box can run): per-step pack -> all-reduce -> all-gather ->
+    population control on the second stream, the weights from the global
+    per-position stale-energy array in their own kernel behind the step
+    kernel, that array's update, its export/import across a restart and the
+    rebalance entry points -- against the serial oracle, with a population
+    spanning several branching CTAs.  (Two real ranks against the oracle:
+    tests/test_multigpu_gpu.py.)"""
+    import torch  # noqa: F401  (maps the NCCL the engine dlopens)
+    from phd_qmclib_b200 import engine
+    p = golden('model_ll_n16.npz')['params']
+    nop, size = int(p[3]), float(p[4])
+    n, wmax, nts, dt, seed = 3000, 4096, 10, 4e-3, 17
+    ini = _ini(np.random.default_rng(23), n, nop, size)
+    st = oracle.DMCState(p, ini, wmax)
+    eng = engine.Engine(_spec(p))
+    eng.comm_init(engine.comm_unique_id(), 1, 0)
+    dp = eng.dmc_params(dt, wmax, n, 0.25, seed, 0.0, size,
+                        energy_mode=energy_mode, local_capacity=wmax)
+    eng.dmc_init(dp, ini)
+    for blk in range(3):
+        a = st.run_block(seed, dt, n, 0.25, nts, 0.0, size,
+                         energy_mode=energy_mode)
+        b = eng.dmc_run_block(nts)
+        assert np.array_equal(a['num_walkers'], b['num_walkers'])
+        for k in ('energy', 'weight', 'ref_energy', 'accum_energy'):
+            assert rel_err(b[k], a[k]) < 1e-10, k
+        assert eng.dmc_rebalance() == 0         # one rank: nothing to move
+        if blk == 1:
+            # restart on a fresh handle, through the exported view of the
+            # global array
+            nx = eng.dmc_get_next()
+            eng.close()
+            eng = engine.Engine(_spec(p))
+            eng.comm_init(engine.comm_unique_id(), 1, 0)
+            eng.dmc_set_state(dp, nx['confs'], nx['energy'], nx['weight'],
+                              nx['scalars'], slot_energy=nx['slot_energy'])
+    assert eng.last_block_stats()['launches'] == 1 + nts * (
+        7 if energy_mode == 0 else 5)
+    _check_state(eng, st)
+    eng.close()
