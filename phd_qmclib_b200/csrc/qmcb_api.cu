@@ -164,6 +164,9 @@ struct qmcb_handle {
     long long *d_counts = nullptr;      // [world] live walkers per rank
     DmcMulti X{};                       // global stale-slot array and the
     bool multi_ready = false;           // per-step collective buffers
+    bool weights_pending = false;       // the last step's weights are still
+                                        // to be formed (by the next branching
+                                        // or by materialize_weights)
     long long rebalance_every = 32;     // in-block check period (steps)
     long long rebalanced_in_block = 0;
 };
@@ -565,6 +568,7 @@ int alloc_dmc(qmcb_handle *h, const qmcb_dmc_params *p,
     C.slot_offset = slot_offset;
     C.energy_mode = p->energy_mode;
     C.defer_weight = (h->comm && p->energy_mode == 0) ? 1 : 0;
+    h->weights_pending = false;
     h->multi_ready = false;     // the global stale-slot array is rebuilt from
                                 // the state about to be loaded
     // the nodes of the block graph hold the constants by value (a
@@ -817,6 +821,25 @@ void fill_scalars(const qmcb_handle *h, const DmcCtl &ctl,
     s->max_num_walkers = h->B.cap;
     s->step = ctl.step;
     s->capacity_hits = ctl.capacity_hits;
+}
+
+// Sharded runs: form the branching weights the last step left pending and
+// bring the global stale-energy array up to date (what the next branching
+// would otherwise do on the fly).  Needed before anything reads or moves the
+// weights: the end of a block, a rebalance.
+int materialize_weights(qmcb_handle *h)
+{
+    if (!h->comm || !h->weights_pending) return QMCB_OK;
+    const int grid = h->sm_count * 4;
+    multi_weight_kernel<<<grid, 256, 0, h->stream>>>(h->B, h->C, h->X);
+    CUDA_TRY(h, cudaEventRecord(h->ev_weighted, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->pc_stream, h->ev_weighted, 0));
+    multi_apply_kernel<<<grid, 256, 0, h->pc_stream>>>(h->X);
+    CUDA_TRY(h, cudaEventRecord(h->ev_controlled, h->pc_stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_controlled, 0));
+    CUDA_TRY(h, cudaGetLastError());
+    h->weights_pending = false;
+    return QMCB_OK;
 }
 
 // Sharded runs: allocate the buffers of the per-step collectives and
@@ -1454,7 +1477,16 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
                            && !do_ssf && !do_den;
     const bool step_fast = step_fast_ok(h);
     auto enqueue_step = [&](int64_t i) -> int {
-        branch_count_kernel<<<B.nblk, BR_THREADS, 0, h->stream>>>(B, h->C);
+        const int fuse = (glob_a && h->weights_pending) ? 1 : 0;
+        branch_count_kernel<<<B.nblk, BR_THREADS, 0, h->stream>>>(B, h->C, X,
+                                                                  fuse);
+        if (fuse) {
+            // the previous step's update of the global array: after its
+            // values have been read above, off the critical path
+            CUDA_TRY(h, cudaEventRecord(h->ev_weighted, h->stream));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->pc_stream, h->ev_weighted, 0));
+            multi_apply_kernel<<<h->sm_count * 4, 256, 0, h->pc_stream>>>(X);
+        }
         branch_fill_kernel<<<B.nblk, BR_THREADS, 0, h->stream>>>(
             B, h->C, L, h->comm ? 0 : 1);
         if (h->comm) {
@@ -1494,17 +1526,10 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
             CUDA_TRY(h, cudaEventRecord(h->step_ev[2 * i + 1], h->stream));
         if (h->comm) {
             CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_controlled, 0));
-            if (glob_a) {
-                const int grid = h->sm_count * 4;
-                multi_weight_kernel<<<grid, 256, 0, h->stream>>>(B, h->C, X);
-                // the update of the global array is off the critical path:
-                // the next reader is the next step's weight kernel, behind
-                // the next ev_controlled of this same stream
-                CUDA_TRY(h, cudaEventRecord(h->ev_weighted, h->stream));
-                CUDA_TRY(h, cudaStreamWaitEvent(h->pc_stream, h->ev_weighted,
-                                                0));
-                multi_apply_kernel<<<grid, 256, 0, h->pc_stream>>>(X);
-            }
+            // the weights of this step's children are formed by the next
+            // branching (branch_count_kernel, fuse_weight) or, at the end of
+            // the block / before a rebalance, by materialize_weights
+            if (glob_a) h->weights_pending = true;
         }
         return QMCB_OK;
     };
@@ -1571,6 +1596,8 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
             }
             if (mx - mn > 1 && ((double) mx > 1.01 * (double) mn
                                 || (double) mx > 0.9 * (double) B.cap)) {
+                rc = materialize_weights(h);
+                if (rc) return rc;
                 int64_t mv = 0;
                 rc = qmcb_dmc_rebalance(h, &mv);
                 if (rc) return rc;
@@ -1579,8 +1606,10 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
         }
     }
     if (h->comm) {
-        // the control stream's last update of the global array is part of
-        // this block
+        // the weights of the last step and the control stream's last update
+        // of the global array are part of this block
+        rc = materialize_weights(h);
+        if (rc) return rc;
         CUDA_TRY(h, cudaEventRecord(h->ev_controlled, h->pc_stream));
         CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_controlled, 0));
     }
@@ -1605,8 +1634,8 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     h->step_host += nts;
-    h->last_launches = 1 + (3 + (h->comm ? (glob_a ? 4 : 2) : 0)) * nts
-                       + est_launches;
+    h->last_launches = 1 + (3 + (h->comm ? (glob_a ? 3 : 2) : 0)) * nts
+                       + (glob_a ? 1 : 0) + est_launches;
     if (density && do_den)
         CUDA_TRY(h, cudaMemcpyAsync(density, h->den_iter,
                                     nts * (size_t) NB * sizeof(double),
@@ -2058,8 +2087,10 @@ int qmcb_dmc_rebalance(qmcb_handle *h, int64_t *moved)
     CUDA_TRY(h, cudaSetDevice(h->device));
     DmcBufs &B = h->B;
     const int R = h->world, me = h->rank, N = h->M.nop;
+    int rc = materialize_weights(h);    // the weights travel with the walkers
+    if (rc) return rc;
     DmcCtl ctl;
-    int rc = read_ctl(h, ctl);
+    rc = read_ctl(h, ctl);
     if (rc) return rc;
     const int par = (int) (ctl.step & 1);
     long long mine = ctl.W_prev;

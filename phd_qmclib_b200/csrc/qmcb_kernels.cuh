@@ -288,14 +288,21 @@ __device__ __forceinline__ bool last_cta_done(unsigned int *counter)
 // K4a+b: clone counts c_s = int(w_s + u_s) (qmc_base/dmc.py:641-643) and, in
 // the last CTA to finish, the scan of the per-CTA sums.
 __global__ void __launch_bounds__(BR_THREADS)
-branch_count_kernel(DmcBufs B, DmcConsts C)
+branch_count_kernel(DmcBufs B, DmcConsts C, DmcMulti X, int fuse_weight)
 {
     const DmcCtl *ctl = B.ctl;
     const int Wp = ctl->W_prev;
     const int par = (int) (ctl->step & 1);
     const uint32_t step = (uint32_t) ctl->step;
     const long long pos0 = ctl->pos_base[par];
-    const double *w = B.weight[par];
+    double *w = B.weight[par];
+    // Sharded runs (fuse_weight): the weights of the walkers about to branch
+    // were left to this kernel by the previous step (DmcConsts::defer_weight);
+    // they come from the global per-position stale-energy array exactly as in
+    // multi_weight_kernel, with the E_ref that drove that step.
+    const double eref_prev = ctl->eref[par ^ 1];
+    const double *e_new = B.energy[par];
+    const long long asize = (long long) X.R * X.cap;
     long long local = 0;
     int base = blockIdx.x * BR_TILE + threadIdx.x * BR_ITEMS;
 #pragma unroll
@@ -306,7 +313,16 @@ branch_count_kernel(DmcBufs B, DmcConsts C)
             double u0, u1;
             rng_uniform2(C.seed, (uint32_t) (pos0 + s), 0u, step,
                          STREAM_BRANCH, u0, u1);
-            double x = w[s] + u0;
+            double ws;
+            if (fuse_weight) {
+                const long long p = pos0 + s;
+                const double e_old = p < asize ? X.aglob[p] : 0.0;
+                ws = exp(-C.dt * ((e_new[s] + e_old) / 2 - eref_prev));
+                w[s] = ws;
+            } else {
+                ws = w[s];
+            }
+            double x = ws + u0;
             c = (x >= (double) B.cap) ? B.cap : (int) x;
             if (c < 0) c = 0;
         }
