@@ -1,19 +1,26 @@
-# GPU-box session: parity tests, smoke, bench, ncu launch list + full capture
-# of the step kernel.  Usage: gpurun -- 'bash scripts/run_gpu_round.sh TAG'
-TAG=${1:-r01}
+# GPU-box session: parity tests, smoke, the four bench lines, the reference arm.
+# Usage: gpurun -- 'bash scripts/run_gpu_round.sh TAG'
+TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi_$TAG.log 2>&1
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > $OUT/pytest_gpu_$TAG.log
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -6 > $OUT/pytest_gpu_$TAG.log
 tail -3 $OUT/pytest_gpu_$TAG.log
-timeout 300 python __graft_entry__.py --smoke > $OUT/smoke_$TAG.log 2>&1; tail -2 $OUT/smoke_$TAG.log
-timeout 900 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; tail -c 3000 $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
-SHORT="python bench.py --steps 1 --warmup 1 --nts 8 --no-cpu"
-timeout 300 $SHORT > $OUT/short_plain_$TAG.log 2>&1 && \
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"dmc_|branch_" -c 300 --csv \
-    --log-file $OUT/launches_$TAG.csv $SHORT > $OUT/ncu_launch_$TAG.log 2>&1
-timeout 300 $SHORT > $OUT/short_plain2_$TAG.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:dmc_step -s 9 -c 2 \
-    -f -o $OUT/prof_step_$TAG $SHORT > $OUT/ncu_full_$TAG.log 2>&1
-tail -3 $OUT/ncu_full_$TAG.log
-ls -la $OUT
+timeout 300 python __graft_entry__.py --smoke > $OUT/smoke_$TAG.log 2>&1; tail -1 $OUT/smoke_$TAG.log
+timeout 900 python bench.py > $OUT/bench_${TAG}_c4.json 2> $OUT/bench_${TAG}_c4.err
+for c in c3_dmc50 c5_est c2_vmc; do
+  timeout 900 python bench.py --config $c > $OUT/bench_${TAG}_$c.json 2> $OUT/bench_${TAG}_$c.err
+done
+timeout 900 python bench.py --impl reference --steps 8 --warmup 3 > $OUT/bench_${TAG}_reference.json 2> $OUT/bench_${TAG}_reference.err
+python - <<PY
+import json
+for c in ('c4', 'c3_dmc50', 'c5_est', 'c2_vmc', 'reference'):
+    try:
+        d = json.load(open('$OUT/bench_${TAG}_%s.json' % c))
+        cb = d.get('cpu_baseline') or {}
+        print(c, '%.4g' % d['value'], d['unit'], 'ms/step %.2f' % d['ms_per_step'],
+              'e2e %.4g' % d['e2e']['value'], 'frac', d.get('roofline', {}).get('frac'),
+              'cpu', cb.get('kind'), cb.get('value'), cb.get('cores'))
+    except Exception as exc:
+        print(c, 'FAILED', exc)
+PY
