@@ -601,3 +601,52 @@ def test_on_device_reblocking_vs_oracle(eng_mod, oracle):
     with pytest.raises(Exception):
         eng.dmc_reblock_get()
     eng.close()
+
+
+@pytest.mark.parametrize('name', ['lat_n50', 'defects_n20', 'odd_n7'])
+def test_shifted_recast_interval_takes_the_exact_path(eng_mod, oracle, name):
+    """The node tables of the per-particle transcendentals cover [0, L]; a
+    sampling that recasts into another interval (here [-L/3, 2L/3]) runs the
+    exact sincospi / exp variants of the DMC step and VMC block kernels.
+    Same parity bar against the oracle."""
+    g = golden('model_' + name + '.npz')
+    p = g['params']
+    nop, size = int(p[3]), float(p[4])
+    lo, hi = -size / 3, 2 * size / 3
+    rng = np.random.default_rng(41)
+    n_ini, wmax, nts = 48, 80, 6
+    ini = np.zeros((n_ini, 2, nop))
+    ini[:, 0] = lo + rng.random((n_ini, nop)) * size
+    st = oracle.DMCState(p, ini, wmax)
+    eng = eng_mod.Engine((p[:12], p[12:19], p[19:]))
+    dp = eng.dmc_params(1e-3, wmax, n_ini, 0.25, 6, lo, hi)
+    eng.dmc_init(dp, ini)
+    for _ in range(2):
+        a = st.run_block(6, 1e-3, n_ini, 0.25, nts, lo, hi)
+        b = eng.dmc_run_block(nts)
+        assert np.array_equal(a['num_walkers'], b['num_walkers'])
+        for k in ('energy', 'weight', 'ref_energy', 'accum_energy'):
+            assert rel_err(b[k], a[k]) < 1e-10, k
+    nw = st.num_walkers
+    nx = eng.dmc_get_next()
+    assert np.allclose(nx['confs'][:, 0], st.prev['confs'][:nw, 0], rtol=0,
+                       atol=1e-9)
+    assert nx['confs'][:, 0].min() >= lo and nx['confs'][:, 0].max() <= hi
+    # VMC on the same interval
+    nch, ns, modes = 24, 10, 6
+    cur = ini[:nch].copy()
+    ln = oracle.model_eval(p, cur, want=('lnpsi',))['lnpsi']
+    eprev, sprev = np.zeros(nch), np.zeros((nch, modes, 3))
+    eng.vmc_init(cur, 0.2, 8, lo, hi, ssf_num_modes=modes)
+    step0 = 0
+    for blk in range(2):
+        first = blk == 0
+        a = oracle.vmc_block(p, 8, 0.2, lo, hi, cur, ln, eprev, sprev, modes,
+                             ns, step0, first)
+        step0 += ns - (1 if first else 0)
+        o = eng.vmc_run_block(ns, series=True)
+        assert np.array_equal(o['move_stat'], a['stat'])
+        assert scaled_err(o['lnpsi'], a['lnpsi']) < 1e-11
+        assert scaled_err(o['energy'], a['energy']) < 1e-11
+        assert np.max(np.abs(o['ssf'] - a['ssf'])) < 1e-9
+    eng.close()
