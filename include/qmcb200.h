@@ -284,9 +284,29 @@ QMCB_API void qmcb_host_free(void *p);
 
 /* ---- multi-GPU (one process per GPU) ------------------------------------ */
 /* 128-byte NCCL unique id, made on rank 0 and broadcast by the caller's own
- * plumbing (torch.distributed).  After qmcb_comm_init the per-step
- * {sum E, W} all-reduce of population control runs over NCCL on the engine's
- * stream. */
+ * plumbing (torch.distributed).  Call qmcb_comm_init BEFORE qmcb_dmc_init /
+ * qmcb_dmc_set_state.  The ranks then hold ordered slabs of ONE ensemble
+ * (rank r: the walkers after those of the lower ranks) and walk exactly the
+ * ensemble a single rank would walk with the same seed:
+ *  - the RNG is keyed by a walker's GLOBAL position in that order (the
+ *    engine derives every rank's first position from the counts of all
+ *    ranks; global_slot_offset is ignored);
+ *  - the reference's per-slot stale-energy array (quirk Q1,
+ *    qmc_base/jastrow/dmc.py:810,936) is kept per global position,
+ *    replicated on every rank, updated each step by an all-gather of 8 bytes
+ *    per slot; `slot_energy` of qmcb_dmc_get_next / qmcb_dmc_set_state is the
+ *    rank's view of it (entries of its walkers; the last rank's entries
+ *    beyond its population are the tail beyond the ensemble);
+ *  - per step one all-reduce of world_size + 2 doubles {sum E, W, counts}
+ *    drives the population control (qmc_base/dmc.py:758-771); both
+ *    collectives run on a second stream next to the step kernel;
+ *  - the per-step series and the estimator tables returned by
+ *    qmcb_dmc_run_block hold GLOBAL values on every rank;
+ *  - inside a block the slabs are evened out (qmcb_dmc_rebalance) whenever
+ *    they drift apart by more than 1 % or near their capacity, unless a
+ *    pure estimator carries per-slot state through the block.
+ * The truncation at capacity (quirk Q8) acts per slab: give local_capacity
+ * slack beyond max_num_walkers / world_size and watch capacity_hits. */
 QMCB_API int qmcb_comm_unique_id(uint8_t id[128]);
 QMCB_API int qmcb_comm_init(qmcb_handle *h, const uint8_t id[128],
                             int32_t world_size, int32_t rank);
