@@ -151,31 +151,49 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                 // e^{i k_m z} of its own particles mode by mode; the sum over
                 // the chain's threads goes through shared memory, VMC_MB
                 // modes per barrier pair.
-                double pc[TB], ps[TB], c1[TB], s1[TB], xs[TB];
+                // Three-term recurrence e^{i(m+1)t} = 2 cos t e^{imt} -
+                // e^{i(m-1)t} (one DFMA per component and mode), exact
+                // re-seed every VMC_RESEED modes; the phases of padding
+                // particles are zero and stay zero, so the sums need no
+                // predicate.
+                double pc[TB], ps[TB], pcp[TB], psp[TB], twoc[TB], xs[TB];
 #pragma unroll
                 for (int q = 0; q < TB; ++q) {
                     xs[q] = z[q] * a.two_over_L;
-                    pc[q] = 1.0; ps[q] = 0.0;
-                    c1[q] = 1.0; s1[q] = 0.0;
-                    if (take && q < nvalid) sincospi(xs[q], &s1[q], &c1[q]);
+                    pc[q] = 0.0; ps[q] = 0.0; pcp[q] = 0.0; psp[q] = 0.0;
+                    twoc[q] = 2.0;
+                    if (take && q < nvalid) {
+                        double s1, c1;
+                        sincospi(xs[q], &s1, &c1);
+                        pc[q] = 1.0;                    // mode 0
+                        pcp[q] = c1; psp[q] = -s1;      // mode -1
+                        twoc[q] = 2.0 * c1;
+                    }
                 }
                 for (int m0 = 0; m0 < a.M; m0 += VMC_MB) {
                     if (take) {
                         if (m0 > 0 && (m0 % VMC_RESEED) == 0) {
 #pragma unroll
                             for (int q = 0; q < TB; ++q)
-                                if (q < nvalid)
+                                if (q < nvalid) {
+                                    double s1, c1;
+                                    sincospi(xs[q], &s1, &c1);
                                     sincospi((double) m0 * xs[q], &ps[q],
                                              &pc[q]);
+                                    pcp[q] = fma(pc[q], c1, ps[q] * s1);
+                                    psp[q] = fma(ps[q], c1, -(pc[q] * s1));
+                                }
                         }
+#pragma unroll
                         for (int j = 0; j < VMC_MB; ++j) {
                             double re = 0.0, im = 0.0;
 #pragma unroll
                             for (int q = 0; q < TB; ++q) {
-                                if (q < nvalid) { re += pc[q]; im += ps[q]; }
-                                double cn = fma(pc[q], c1[q], -(ps[q] * s1[q]));
-                                ps[q] = fma(ps[q], c1[q], pc[q] * s1[q]);
-                                pc[q] = cn;
+                                re += pc[q]; im += ps[q];
+                                const double cn = fma(twoc[q], pc[q], -pcp[q]);
+                                const double sn = fma(twoc[q], ps[q], -psp[q]);
+                                pcp[q] = pc[q]; psp[q] = ps[q];
+                                pc[q] = cn; ps[q] = sn;
                             }
                             part[x.I * VMC_MB + j] = make_double2(re, im);
                         }
