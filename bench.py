@@ -791,12 +791,19 @@ def run_vmc(name, cfg, args, D):
     h_confs = engine.pinned_empty((nch, 2, n))
     h_confs[:] = confs
 
+    # results land in page-locked arrays allocated once (the chains come
+    # back into the buffer the next block is initialised from)
+    h_out = {'accept_rate': engine.pinned_empty((nch,)),
+             'sum_energy': engine.pinned_empty((nch, 2))}
+    if M:
+        h_out['sum_ssf'] = engine.pinned_empty((nch, M, 3))
+    h_ln = engine.pinned_empty((nch,))
+
     def e2e_step():
         eng.vmc_init(h_confs, spread, 1, 0.0, float(n), ssf_num_modes=M,
                      chain_offset=rank * nch)
-        o = eng.vmc_run_block(ns, series=False, sums=True)
-        c2, _ = eng.vmc_get_state()
-        h_confs[:] = c2
+        o = eng.vmc_run_block(ns, series=False, sums=True, out=h_out)
+        eng.vmc_get_state(out=(h_confs, h_ln))
         return o
 
     e2e_step()
@@ -812,7 +819,8 @@ def run_vmc(name, cfg, args, D):
            'h2d_bytes_per_step': int(h2d * world),
            'd2h_bytes_per_step': int(d2h * world),
            'timing': 'host wall clock around K x (vmc_init from pinned host '
-                     '+ run_block with per-chain sums to host + get_state), '
+                     '+ run_block with per-chain sums to pinned host + '
+                     'get_state to pinned host), '
                      'max over ranks; the first step of a re-initialised '
                      'block re-evaluates the initial configuration',
            'ms_per_step': wall * 1e3 / args.steps}

@@ -617,6 +617,17 @@ def main():
         gen_dmc_stat_pure(mrbp, 'lat_n50', SPECS['lat_n50'], n_target=512,
                           wmax=640, dt=1e-3, nts=128, nblocks=160, burn=24,
                           seed=21)
+    if 'statpure100' in which:
+        # BASELINE configs[3] model (N=100, dt of the headline bench)
+        gen_dmc_stat_pure(mrbp, 'lat_n100', SPECS['lat_n100'], n_target=256,
+                          wmax=320, dt=6.25e-4, nts=128, nblocks=96, burn=32,
+                          seed=22)
+    if 'statpure200' in which:
+        # BASELINE configs[4] model (N=200, deep lattice), S(k) and density
+        gen_dmc_stat_pure(mrbp, 'deep_n200', SPECS['deep_n200'],
+                          n_target=128, wmax=160, dt=1e-3, nts=128,
+                          nblocks=80, burn=24, seed=23, num_modes=8,
+                          num_bins=100)
     if 'stat' in which:
         gen_dmc_stat(mrbp, 'll_n16', SPECS['ll_n16'], n_target=512, wmax=640,
                      dt=2e-3, nts=256, nblocks=48, burn=12, seed=11)

@@ -2228,20 +2228,30 @@ int qmcb_vmc_init(qmcb_handle *h, const qmcb_vmc_params *params,
     CUDA_TRY(h, cudaFuncSetAttribute(
                     vmc_block_kernel<true>,
                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) vsm));
-    free_vmc(h);
-    h->vp = *params;
     const size_t C = (size_t) num_chains;
-    CUDA_TRY(h, cudaMalloc(&h->V.confs, C * 2 * N * sizeof(double)));
-    CUDA_TRY(h, cudaMalloc(&h->V.lnpsi, C * sizeof(double)));
-    CUDA_TRY(h, cudaMalloc(&h->V.eprev, C * sizeof(double)));
-    CUDA_TRY(h, cudaMalloc(&h->vmc_sum_e, C * 2 * sizeof(double)));
-    CUDA_TRY(h, cudaMalloc(&h->vmc_acc, C * sizeof(double)));
-    if (M) {
-        CUDA_TRY(h, cudaMalloc(&h->V.ssfprev, C * M * 3 * sizeof(double)));
-        CUDA_TRY(h, cudaMalloc(&h->vmc_sum_ssf, C * M * 3 * sizeof(double)));
+    // a re-initialisation of the same shape (chains handed back from the
+    // host block after block) keeps its device buffers
+    const bool same_shape = h->vmc_ready && h->vmc_chains == num_chains
+                            && h->vp.ssf_num_modes == M;
+    if (!same_shape) {
+        free_vmc(h);
+        CUDA_TRY(h, cudaMalloc(&h->V.confs, C * 2 * N * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc(&h->V.lnpsi, C * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc(&h->V.eprev, C * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc(&h->vmc_sum_e, C * 2 * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc(&h->vmc_acc, C * sizeof(double)));
+        if (M) {
+            CUDA_TRY(h, cudaMalloc(&h->V.ssfprev,
+                                   C * M * 3 * sizeof(double)));
+            CUDA_TRY(h, cudaMalloc(&h->vmc_sum_ssf,
+                                   C * M * 3 * sizeof(double)));
+        }
+    }
+    h->vmc_ready = false;
+    h->vp = *params;
+    if (M)
         CUDA_TRY(h, cudaMemsetAsync(h->V.ssfprev, 0,
                                     C * M * 3 * sizeof(double), h->stream));
-    }
     CUDA_TRY(h, cudaMemsetAsync(h->V.eprev, 0, C * sizeof(double),
                                 h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->V.confs, confs,
@@ -2253,21 +2263,26 @@ int qmcb_vmc_init(qmcb_handle *h, const qmcb_vmc_params *params,
     a.confs = h->V.confs; a.nconf = num_chains; a.lnpsi = h->V.lnpsi;
     int rc = launch_model_eval(h, a, true, false);
     if (rc) return rc;
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     // the table path of the block kernel needs every position in [0, L]
     h->vmc_fast = h->M.tt.zt != nullptr && params->lower_bound == 0.0
                   && params->upper_bound - params->lower_bound == h->M.L;
+    int outside = 0;
     if (h->vmc_fast) {
-        const size_t row = (size_t) N;
-        for (size_t c = 0; c < C && h->vmc_fast; ++c) {
-            const double *zr = confs + c * 2 * row;
-            for (size_t i = 0; i < row; ++i)
-                if (!(zr[i] >= 0.0 && zr[i] <= h->M.L)) {
-                    h->vmc_fast = false;
-                    break;
-                }
-        }
+        rc = ensure_scratch(h, 8);
+        if (rc) return rc;
+        int *d_flag = reinterpret_cast<int *>(h->d_scratch);
+        CUDA_TRY(h, cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
+        const long long total = (long long) C * N;
+        const int grid = (int) std::min<long long>(
+            (total + 255) / 256, (long long) h->sm_count * 16);
+        positions_outside_kernel<<<grid, 256, 0, h->stream>>>(
+            h->V.confs, (long long) C, N, h->M.L, d_flag);
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaMemcpyAsync(&outside, d_flag, sizeof(int),
+                                    cudaMemcpyDeviceToHost, h->stream));
     }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (outside) h->vmc_fast = false;
     h->vmc_chains = num_chains;
     h->vmc_gstep = 0;
     h->vmc_first = 1;

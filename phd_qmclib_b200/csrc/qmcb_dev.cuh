@@ -639,7 +639,7 @@ __device__ __forceinline__ void pair_tile(
                 inv = ok ? inv : 0.0;
                 if (LN) {
                     den_f[c1] = ok ? den_f[c1] : 1.0;
-                    den_n = ok ? den_n : 1.0;
+                    den = ok ? den : 1.0;
                     acc.npair += ok ? 1 : 0;
                     acc.nnear += (ok && near) ? 1 : 0;
                 }
@@ -654,7 +654,7 @@ __device__ __forceinline__ void pair_tile(
             }
             if (LN) {
                 acc.pf *= near ? 1.0 : fabs(den_f[c1]);
-                acc.pn *= near ? fabs(den_n) : 1.0;
+                acc.pn *= fabs(den);       // every pair (see group_eval)
             }
         }
         if (EF) { *pq = fc; pq += nbp; }
@@ -767,7 +767,7 @@ __device__ __forceinline__ void pair_tile_lean(
                 inv = ok ? inv : 0.0;
                 if (LN) {
                     den_f[c1] = ok ? den_f[c1] : 1.0;
-                    den_n = ok ? den_n : 1.0;
+                    den = ok ? den : 1.0;
                     acc.nnear += (ok && near) ? 1 : 0;
                 }
             } else if (LN) {
@@ -780,8 +780,11 @@ __device__ __forceinline__ void pair_tile_lean(
                 acc.K = fma(inv, inv, acc.K);
             }
             if (LN) {
+                // pn collects EVERY pair's denominator here (the selected
+                // one needs no second select); the far ones are divided out
+                // in the logarithm (group_eval)
                 acc.pf *= near ? 1.0 : fabs(den_f[c1]);
-                acc.pn *= near ? fabs(den_n) : 1.0;
+                acc.pn *= fabs(den);
             }
         }
         if (EF) { *pq = fc; pq += nbp; }
@@ -960,9 +963,11 @@ __device__ __forceinline__ void group_eval(const DevModel &M,
             lpart = ln1;
             if (!M.is_ideal) {
                 const int nfar = acc.npair - acc.nnear;
-                lpart += M.beta * (log(acc.pf) + acc.ef * LN2
-                                   + nfar * M.ln_gam)
-                         + (log(acc.pn) + acc.en * LN2)
+                // pn holds the denominators of ALL pairs, pf those of the
+                // far ones: ln(near product) = ln pn - ln pf
+                const double lf = log(acc.pf) + acc.ef * LN2;
+                lpart += M.beta * (lf + nfar * M.ln_gam)
+                         + ((log(acc.pn) + acc.en * LN2) - lf)
                          + acc.nnear * M.ln_am;
             }
             sm.red(g, 1)[I] = lpart;

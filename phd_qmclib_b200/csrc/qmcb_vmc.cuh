@@ -45,6 +45,24 @@ struct VmcArgs {
 // FAST: node-table transcendentals (TrigTab); needs every position in
 // [0, L]: the recast interval equal to the supercell and initial positions
 // inside it (checked by the host).
+// 1 in *flag when some position of row 0 of `confs` [C][2][N] is outside
+// [0, L] (NaN included): the table path of the block kernel then stays off.
+__global__ void positions_outside_kernel(const double *__restrict__ confs,
+                                         long long nchains, int nop, double L,
+                                         int *flag)
+{
+    const long long total = nchains * nop;
+    bool bad = false;
+    for (long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+         t < total; t += (long long) gridDim.x * blockDim.x) {
+        const long long c = t / nop;
+        const double z = confs[c * 2 * nop + (t - c * nop)];
+        bad |= !(z >= 0.0 && z <= L);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0)
+        atomicOr(flag, 1);
+}
+
 template <bool FAST>
 __global__ void __launch_bounds__(256, 2)
 vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,

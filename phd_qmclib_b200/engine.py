@@ -450,17 +450,34 @@ class Engine:
         self._vmc_chains = confs.shape[0]
         self._vmc_modes = ssf_num_modes
 
-    def vmc_run_block(self, ns, series=True, sums=False):
+    def vmc_run_block(self, ns, series=True, sums=False, out=None):
+        """One block of ``ns`` steps.  ``out`` may hold preallocated result
+        arrays by name (e.g. page-locked ones from `pinned_empty`, for a
+        full-rate copy back); the others are allocated here."""
         c, m = self._vmc_chains, self._vmc_modes
+        given = out or {}
+
+        def buf(name, shape, dtype=np.float64):
+            a = given.get(name)
+            if a is None:
+                return np.empty(shape, dtype=dtype)
+            if (a.shape != tuple(shape) or a.dtype != np.dtype(dtype)
+                    or not a.flags.c_contiguous or not a.flags.writeable):
+                raise ValueError(f'out[{name!r}] must be a writeable '
+                                 f'C-contiguous {np.dtype(dtype)} array of '
+                                 f'shape {tuple(shape)}')
+            return a
+
         out = {}
         if series:
-            out.update(lnpsi=np.empty((c, ns)), energy=np.empty((c, ns)),
-                       move_stat=np.empty((c, ns), dtype=np.uint8),
-                       ssf=np.empty((c, ns, m, 3)) if m else None)
-        out['accept_rate'] = np.empty(c)
+            out.update(lnpsi=buf('lnpsi', (c, ns)),
+                       energy=buf('energy', (c, ns)),
+                       move_stat=buf('move_stat', (c, ns), np.uint8),
+                       ssf=buf('ssf', (c, ns, m, 3)) if m else None)
+        out['accept_rate'] = buf('accept_rate', (c,))
         if sums:
-            out['sum_energy'] = np.empty((c, 2))
-            out['sum_ssf'] = np.empty((c, m, 3)) if m else None
+            out['sum_energy'] = buf('sum_energy', (c, 2))
+            out['sum_ssf'] = buf('sum_ssf', (c, m, 3)) if m else None
         rc = self._L.qmcb_vmc_run_block(
             self._h, ns, ptr(out.get('lnpsi')), ptr(out.get('energy')),
             ptr(out.get('move_stat')), ptr(out.get('ssf')),
@@ -493,9 +510,20 @@ class Engine:
         self._check(rc, 'qmcb_vmc_one_body_density')
         return out
 
-    def vmc_get_state(self):
+    def vmc_get_state(self, out=None):
+        """(confs (C, 2, N), ln|Psi| (C,)) of the current states; ``out`` may
+        be a preallocated (confs, lnpsi) pair to fill."""
         c = self._vmc_chains
-        confs, ln = np.empty((c, 2, self.nop)), np.empty(c)
+        if out is not None:
+            confs, ln = out
+            for a, shape in ((confs, (c, 2, self.nop)), (ln, (c,))):
+                if (a.shape != shape or a.dtype != np.float64
+                        or not a.flags.c_contiguous):
+                    raise ValueError('out must hold C-contiguous float64 '
+                                     f'arrays of shape {(c, 2, self.nop)} '
+                                     f'and {(c,)}')
+        else:
+            confs, ln = np.empty((c, 2, self.nop)), np.empty(c)
         rc = self._L.qmcb_vmc_get_state(self._h, ptr(confs), ptr(ln))
         self._check(rc, 'qmcb_vmc_get_state')
         return confs, ln

@@ -362,6 +362,58 @@ def test_vmc_blocks_vs_oracle(eng_mod, oracle, name, nch, ns, modes, spread,
     eng.close()
 
 
+def test_vmc_reinit_reuses_buffers_and_fills_caller_arrays(eng_mod, oracle):
+    """`vmc_init` of the same shape on a live engine (the end-to-end loop of
+    bench.py) must behave like a fresh engine; results can land in
+    caller-owned page-locked arrays; a start outside [0, L] (legal: the
+    reference only wraps proposals) turns the node tables off, not the
+    answer."""
+    g = golden('model_lat_n50.npz')
+    p = g['params']
+    nop, size = int(p[3]), float(p[4])
+    nch, ns, M = 37, 6, 9
+    rng = np.random.default_rng(5)
+    eng = eng_mod.Engine((p[:12], p[12:19], p[19:]))
+    out = {'accept_rate': eng_mod.pinned_empty((nch,)),
+           'sum_energy': eng_mod.pinned_empty((nch, 2)),
+           'sum_ssf': eng_mod.pinned_empty((nch, M, 3)),
+           'lnpsi': eng_mod.pinned_empty((nch, ns)),
+           'energy': eng_mod.pinned_empty((nch, ns)),
+           'move_stat': eng_mod.pinned_empty((nch, ns), np.uint8),
+           'ssf': eng_mod.pinned_empty((nch, ns, M, 3))}
+    state = (eng_mod.pinned_empty((nch, 2, nop)), eng_mod.pinned_empty((nch,)))
+    for trial, shift in enumerate((0.0, 0.0, 0.75)):
+        ini = np.zeros((nch, 2, nop))
+        ini[:, 0] = rng.random((nch, nop)) * size
+        ini[3, 0, 7] = size + shift if shift else ini[3, 0, 7]
+        ini[5, 0, 0] = -shift if shift else ini[5, 0, 0]
+        eng.vmc_init(ini, 0.2, 31 + trial, 0.0, size, ssf_num_modes=M,
+                     chain_offset=2)
+        ln = oracle.model_eval(p, ini, want=('lnpsi',))['lnpsi']
+        cur = ini.copy()
+        a = oracle.vmc_block(p, 31 + trial, 0.2, 0.0, size, cur, ln,
+                             np.zeros(nch), np.zeros((nch, M, 3)), M, ns, 0,
+                             True, chain_offset=2)
+        o = eng.vmc_run_block(ns, series=True, sums=True, out=out)
+        for key in out:
+            assert o[key] is out[key]
+        assert np.array_equal(o['move_stat'], a['stat'])
+        assert scaled_err(o['lnpsi'], a['lnpsi']) < 1e-12
+        assert scaled_err(o['energy'], a['energy']) < 1e-11
+        assert np.max(np.abs(o['ssf'] - a['ssf'])) < 1e-9
+        assert np.allclose(o['sum_ssf'], a['ssf'].sum(axis=1), rtol=1e-9,
+                           atol=1e-8)
+        confs, lnpsi = eng.vmc_get_state(out=state)
+        assert confs is state[0] and lnpsi is state[1]
+        assert np.allclose(confs[:, 0], cur[:, 0], rtol=0, atol=1e-12)
+    with pytest.raises(ValueError):
+        eng.vmc_run_block(ns, series=False, sums=True,
+                          out={'sum_energy': np.empty((nch, 3))})
+    with pytest.raises(ValueError):
+        eng.vmc_get_state(out=(np.empty((nch, 2, nop + 1)), np.empty(nch)))
+    eng.close()
+
+
 @pytest.mark.parametrize('kwargs', [
     # every cell is a defect (defects_sep == 1 with V_defect != V0)
     dict(lattice_depth=40.0, lattice_ratio=1, interaction_strength=2,

@@ -377,15 +377,17 @@ def test_vmc_chain_recording_and_obd_hook(oracle):
     c.engine.close()
 
 
-def test_dmc_pure_estimators_n50_vs_reference_run():
-    """Statistical parity at a BASELINE particle number (configs[2] model,
-    N=50) for the PURE (forward-walking) S(k) and density estimators and the
-    energy: the engine against a frozen run of the live reference
+@pytest.mark.parametrize('name', ['lat_n50', 'lat_n100', 'deep_n200'])
+def test_dmc_pure_estimators_vs_reference_run(name):
+    """Statistical parity at the BASELINE particle numbers (configs[2], [3]
+    and [4] models: N=50, N=100 at the headline time step, N=200 in the deep
+    lattice) for the PURE (forward-walking) S(k) and density estimators and
+    the energy: the engine against a frozen run of the live reference
     (oracle/make_golden.py: gen_dmc_stat_pure, `jit_parallel=True` like
     Proc.sampling), reduced per block as qmc_exec/dmc/proc.py:304-350 does
     (last step of a block, weighted by that step's population)."""
     from phd_qmclib_b200 import dmc
-    g = golden('dmc_stat_pure_lat_n50.npz')
+    g = golden(f'dmc_stat_pure_{name}.npz')
     p = g['params']
     nop = int(p[3])
     nts, nblocks, burn = int(g['nts']), int(g['nblocks']), int(g['burn'])
@@ -424,7 +426,7 @@ def test_dmc_pure_estimators_n50_vs_reference_run():
     e_ref, err_ref = ratio_mean_error(g['block_energy'], g['block_weight'])
     err_ref = max(err_ref, float(g['ref_energy_err']))
     z = (e_eng - e_ref) / np.hypot(err_ref, err_eng)
-    print(f'dmc pure N=50 E/N: {e_eng / nop:.5f} vs {e_ref / nop:.5f}, '
+    print(f'dmc pure {name} E/N: {e_eng / nop:.5f} vs {e_ref / nop:.5f}, '
           f'z = {z:+.2f}')
     assert abs(z) < 4
     rs, rn = g['block_ssf_last'][:, :, 0], g['block_walkers_last']
@@ -448,8 +450,8 @@ def test_dmc_pure_estimators_n50_vs_reference_run():
     zd = np.array(zd)
     print(f'pure density z: max {np.abs(zd).max():.2f} rms '
           f'{np.sqrt(np.mean(zd ** 2)):.2f}')
-    # 50 bins: the largest of 50 normal deviates stays below 4.5, their rms
-    # near 1
+    # 50-100 bins: the largest of that many normal deviates stays below 4.5,
+    # their rms near 1
     assert np.abs(zd).max() < 4.5 and np.sqrt(np.mean(zd ** 2)) < 1.6
     # each walker contributes N counts
     assert np.allclose(d_last.sum(axis=1) / n_last, nop, rtol=0.05)
