@@ -619,8 +619,10 @@ def main():
                           seed=21)
     if 'statpure100' in which:
         # BASELINE configs[3] model (N=100, dt of the headline bench)
+        # (blocks of tau = 0.16: shorter ones leave the density bins of
+        # neighbouring blocks correlated beyond what 96 blocks can resolve)
         gen_dmc_stat_pure(mrbp, 'lat_n100', SPECS['lat_n100'], n_target=256,
-                          wmax=320, dt=6.25e-4, nts=128, nblocks=96, burn=32,
+                          wmax=320, dt=6.25e-4, nts=256, nblocks=96, burn=16,
                           seed=22)
     if 'statpure200' in which:
         # BASELINE configs[4] model (N=200, deep lattice), S(k) and density

@@ -12,8 +12,10 @@
 
 namespace qmcb {
 
-constexpr int VMC_MB = 8;       // S(k) modes reduced per CTA barrier pair
-constexpr int VMC_RESEED = 64;  // exact phase re-seed period (modes)
+constexpr int VMC_MB = 10;      // S(k) modes per batch (2 * VMC_MB * nb <= 20 * nbp)
+constexpr int VMC_RESEED = 60;  // exact phase re-seed period (modes; multiple of VMC_MB)
+
+static_assert(VMC_RESEED % VMC_MB == 0, "re-seed at batch boundaries");
 
 struct VmcState {
     double *confs;      // [C][2][N]   row 0 positions, row 1 drift
@@ -87,8 +89,9 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
             e_prev = S.eprev[c];
         }
         const uint32_t gc = (uint32_t) (a.chain_offset + c);
-        // S(k) partials [nb][VMC_MB] reuse the walker's pair tables, which
-        // are dead between two evaluations (8 * nb <= 20 * nbp double2)
+        // S(k) partials, two buffers of [nb][VMC_MB], reuse the walker's pair
+        // tables, which are dead between two evaluations (2 * VMC_MB * nb <=
+        // 20 * nbp double2)
         double2 *part = reinterpret_cast<double2 *>(sm.tab(x.g));
         for (long long st = 0; st < a.ns; ++st) {
             const bool ini = a.first && st == 0;
@@ -188,7 +191,15 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                         twoc[q] = 2.0 * c1;
                     }
                 }
-                for (int m0 = 0; m0 < a.M; m0 += VMC_MB) {
+                // The partials are double-buffered: one CTA barrier per
+                // batch.  A chain whose proposal was rejected re-adds the
+                // parts of its unchanged state AHEAD of the barrier (its
+                // global loads overlap the other chains' phase arithmetic);
+                // the block sums are accumulated with fire-and-forget
+                // reductions (one adder per address: the order is fixed).
+                int buf = 0;
+                for (int m0 = 0; m0 < a.M; m0 += VMC_MB, buf ^= 1) {
+                    double2 *pb = part + buf * (nb * VMC_MB);
                     if (take) {
                         if (m0 > 0 && (m0 % VMC_RESEED) == 0) {
 #pragma unroll
@@ -213,38 +224,52 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                                 pcp[q] = pc[q]; psp[q] = ps[q];
                                 pc[q] = cn; ps[q] = sn;
                             }
-                            part[x.I * VMC_MB + j] = make_double2(re, im);
+                            pb[x.I * VMC_MB + j] = make_double2(re, im);
+                        }
+                    } else if (active) {
+                        for (int j = x.I; j < VMC_MB && m0 + j < a.M;
+                             j += nb) {
+                            const int m = m0 + j;
+                            const double *sp = S.ssfprev + (c * a.M + m) * 3;
+                            const double v0 = sp[0], v1 = sp[1], v2 = sp[2];
+                            if (a.sum_ssf) {
+                                double *ss = a.sum_ssf + (c * a.M + m) * 3;
+                                atomicAdd(ss, v0); atomicAdd(ss + 1, v1);
+                                atomicAdd(ss + 2, v2);
+                            }
+                            if (a.out_ssf) {
+                                double *os = a.out_ssf
+                                    + ((c * a.ns + st) * a.M + m) * 3;
+                                os[0] = v0; os[1] = v1; os[2] = v2;
+                            }
                         }
                     }
                     __syncthreads();
-                    for (int j = x.I; active && j < VMC_MB && m0 + j < a.M;
+                    for (int j = x.I; take && j < VMC_MB && m0 + j < a.M;
                          j += nb) {
                         const int m = m0 + j;
-                        double *sp = S.ssfprev + (c * a.M + m) * 3;
-                        double v0, v1, v2;
-                        if (take) {
-                            double re = 0.0, im = 0.0;
-                            for (int t = 0; t < nb; ++t) {
-                                double2 pp = part[t * VMC_MB + j];
-                                re += pp.x; im += pp.y;
-                            }
-                            v0 = fma(re, re, im * im); v1 = re; v2 = im;
-                            sp[0] = v0; sp[1] = v1; sp[2] = v2;
-                        } else {
-                            v0 = sp[0]; v1 = sp[1]; v2 = sp[2];
+                        double re = 0.0, im = 0.0;
+                        for (int t = 0; t < nb; ++t) {
+                            double2 pp = pb[t * VMC_MB + j];
+                            re += pp.x; im += pp.y;
                         }
+                        const double v0 = fma(re, re, im * im);
+                        double *sp = S.ssfprev + (c * a.M + m) * 3;
+                        sp[0] = v0; sp[1] = re; sp[2] = im;
                         if (a.sum_ssf) {
                             double *ss = a.sum_ssf + (c * a.M + m) * 3;
-                            ss[0] += v0; ss[1] += v1; ss[2] += v2;
+                            atomicAdd(ss, v0); atomicAdd(ss + 1, re);
+                            atomicAdd(ss + 2, im);
                         }
                         if (a.out_ssf) {
                             double *os = a.out_ssf
                                 + ((c * a.ns + st) * a.M + m) * 3;
-                            os[0] = v0; os[1] = v1; os[2] = v2;
+                            os[0] = v0; os[1] = re; os[2] = im;
                         }
                     }
-                    __syncthreads();
                 }
+                // the partials alias the pair tables of the next evaluation
+                __syncthreads();
             }
         }
         if (active) {
