@@ -89,7 +89,7 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
             e_prev = S.eprev[c];
         }
         const uint32_t gc = (uint32_t) (a.chain_offset + c);
-        // S(k) partials, two buffers of [nb][VMC_MB], reuse the walker's pair
+        // S(k) partials, two buffers of [VMC_MB][nb], reuse the walker's pair
         // tables, which are dead between two evaluations (2 * VMC_MB * nb <=
         // 20 * nbp double2)
         double2 *part = reinterpret_cast<double2 *>(sm.tab(x.g));
@@ -224,7 +224,7 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                                 pcp[q] = pc[q]; psp[q] = ps[q];
                                 pc[q] = cn; ps[q] = sn;
                             }
-                            pb[x.I * VMC_MB + j] = make_double2(re, im);
+                            pb[j * nb + x.I] = make_double2(re, im);
                         }
                     } else if (active) {
                         for (int j = x.I; j < VMC_MB && m0 + j < a.M;
@@ -248,11 +248,17 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                     for (int j = x.I; take && j < VMC_MB && m0 + j < a.M;
                          j += nb) {
                         const int m = m0 + j;
-                        double re = 0.0, im = 0.0;
-                        for (int t = 0; t < nb; ++t) {
-                            double2 pp = pb[t * VMC_MB + j];
-                            re += pp.x; im += pp.y;
+                        // two interleaved running sums (fixed order)
+                        const double2 *pj = pb + j * nb;
+                        double re = 0.0, im = 0.0, re1 = 0.0, im1 = 0.0;
+                        int t = 0;
+                        for (; t + 1 < nb; t += 2) {
+                            const double2 p0 = pj[t], p1 = pj[t + 1];
+                            re += p0.x; im += p0.y;
+                            re1 += p1.x; im1 += p1.y;
                         }
+                        if (t < nb) { re += pj[t].x; im += pj[t].y; }
+                        re += re1; im += im1;
                         const double v0 = fma(re, re, im * im);
                         double *sp = S.ssfprev + (c * a.M + m) * 3;
                         sp[0] = v0; sp[1] = re; sp[2] = im;
