@@ -75,6 +75,11 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
     const int N = M.nop, nb = M.nb;
     const bool vec_ok = (N % 2) == 0;
     const int nvalid = min(TB, N - TB * x.I);
+    // accepted-chain masks of two consecutive steps (compacted S(k) phases)
+    __shared__ unsigned take_mask[2];
+    const bool compact = geom.G <= 32 && a.M > 0;
+    if (threadIdx.x < 2) take_mask[threadIdx.x] = 0u;
+    __syncthreads();
     for (long long base = (long long) blockIdx.x * geom.G; base < a.nchains;
          base += (long long) gridDim.x * geom.G) {
         const long long c = base + x.g;
@@ -177,13 +182,43 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                 // re-seed every VMC_RESEED modes; the phases of padding
                 // particles are zero and stay zero, so the sums need no
                 // predicate.
+                // The phase work is COMPACTED: with ~half of the proposals
+                // rejected, a warp of chain threads would run it half empty.
+                // The accepted chains park their new positions in the state
+                // array and the first (accepted chains) x nb threads of the
+                // CTA take one (chain, particle block) unit each: whole warps
+                // work, the others skip.  Pairing by rank from a mask word.
+                const int par = (int) (st & 1);
+                bool prod = take;
+                int ug = x.g, ub = x.I, unv = nvalid;
+                double zz[TB];
+#pragma unroll
+                for (int q = 0; q < TB; ++q) zz[q] = z[q];
+                if (compact) {
+                    if (active && take) {
+                        store4(S.confs + c * 2 * N, x.I, nvalid, vec_ok, z);
+                        if (x.I == 0) atomicOr(&take_mask[par], 1u << x.g);
+                    }
+                    __syncthreads();
+                    const unsigned tk = take_mask[par];
+                    const int k = (int) threadIdx.x / nb;
+                    ub = (int) threadIdx.x - k * nb;
+                    prod = k < __popc(tk);
+                    ug = prod ? (int) __fns(tk, 0u, k + 1) : 0;
+                    unv = min(TB, N - TB * ub);
+                    if (prod)
+                        load4(S.confs + (base + ug) * 2 * N, ub, unv, vec_ok,
+                              zz);
+                    if (threadIdx.x == 0) take_mask[par ^ 1] = 0u;
+                }
+                double2 *upart = reinterpret_cast<double2 *>(sm.tab(ug));
                 double pc[TB], ps[TB], pcp[TB], psp[TB], twoc[TB], xs[TB];
 #pragma unroll
                 for (int q = 0; q < TB; ++q) {
-                    xs[q] = z[q] * a.two_over_L;
+                    xs[q] = zz[q] * a.two_over_L;
                     pc[q] = 0.0; ps[q] = 0.0; pcp[q] = 0.0; psp[q] = 0.0;
                     twoc[q] = 2.0;
-                    if (take && q < nvalid) {
+                    if (prod && q < unv) {
                         double s1, c1;
                         sincospi(xs[q], &s1, &c1);
                         pc[q] = 1.0;                    // mode 0
@@ -200,11 +235,12 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                 int buf = 0;
                 for (int m0 = 0; m0 < a.M; m0 += VMC_MB, buf ^= 1) {
                     double2 *pb = part + buf * (nb * VMC_MB);
-                    if (take) {
+                    if (prod) {
+                        double2 *upb = upart + buf * (nb * VMC_MB);
                         if (m0 > 0 && (m0 % VMC_RESEED) == 0) {
 #pragma unroll
                             for (int q = 0; q < TB; ++q)
-                                if (q < nvalid) {
+                                if (q < unv) {
                                     double s1, c1;
                                     sincospi(xs[q], &s1, &c1);
                                     sincospi((double) m0 * xs[q], &ps[q],
@@ -224,9 +260,10 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                                 pcp[q] = pc[q]; psp[q] = ps[q];
                                 pc[q] = cn; ps[q] = sn;
                             }
-                            pb[j * nb + x.I] = make_double2(re, im);
+                            upb[j * nb + ub] = make_double2(re, im);
                         }
-                    } else if (active) {
+                    }
+                    if (active && !take) {
                         for (int j = x.I; j < VMC_MB && m0 + j < a.M;
                              j += nb) {
                             const int m = m0 + j;
@@ -292,6 +329,7 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                 }
             }
         }
+        if (threadIdx.x < 2) take_mask[threadIdx.x] = 0u;   // next pass
         __syncthreads();
     }
 }
