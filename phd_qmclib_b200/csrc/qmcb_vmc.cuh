@@ -87,6 +87,8 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
         double z[TB] = {}, Fcur[TB] = {};
         double ln_cur = 0.0, e_prev = 0.0, se = 0.0, se2 = 0.0;
         long long nacc = 0;
+        int nstay = 0;      // steps the current state has not yet been added
+                            // to the S(k) block sums for
         if (active) {
             load4(S.confs + c * 2 * N, x.I, nvalid, vec_ok, z);
             load4(S.confs + c * 2 * N + N, x.I, nvalid, vec_ok, Fcur);
@@ -227,11 +229,9 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                     }
                 }
                 // The partials are double-buffered: one CTA barrier per
-                // batch.  A chain whose proposal was rejected re-adds the
-                // parts of its unchanged state AHEAD of the barrier (its
-                // global loads overlap the other chains' phase arithmetic);
-                // the block sums are accumulated with fire-and-forget
-                // reductions (one adder per address: the order is fixed).
+                // batch.  The block sums are accumulated with fire-and-forget
+                // reductions (the adds to one address are a barrier apart:
+                // their order is fixed).
                 int buf = 0;
                 for (int m0 = 0; m0 < a.M; m0 += VMC_MB, buf ^= 1) {
                     double2 *pb = part + buf * (nb * VMC_MB);
@@ -263,28 +263,41 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                             upb[j * nb + ub] = make_double2(re, im);
                         }
                     }
-                    if (active && !take) {
+                    // Block sums, lazily: a state that stays for n steps
+                    // adds n times its parts when it is replaced (or at the
+                    // end of the block), so a rejected proposal costs no
+                    // memory traffic here.  The replaced state's parts are
+                    // fetched ahead of the barrier, in flight while the
+                    // phases of this batch are produced.
+                    double o0 = 0.0, o1 = 0.0, o2 = 0.0;
+                    const bool flush = take && nstay > 0 && a.sum_ssf;
+                    if (flush && x.I < VMC_MB && m0 + x.I < a.M) {
+                        const double *sp = S.ssfprev
+                            + (c * a.M + m0 + x.I) * 3;
+                        o0 = sp[0]; o1 = sp[1]; o2 = sp[2];
+                    }
+                    if (a.out_ssf && active && !take) {
                         for (int j = x.I; j < VMC_MB && m0 + j < a.M;
                              j += nb) {
                             const int m = m0 + j;
                             const double *sp = S.ssfprev + (c * a.M + m) * 3;
-                            const double v0 = sp[0], v1 = sp[1], v2 = sp[2];
-                            if (a.sum_ssf) {
-                                double *ss = a.sum_ssf + (c * a.M + m) * 3;
-                                atomicAdd(ss, v0); atomicAdd(ss + 1, v1);
-                                atomicAdd(ss + 2, v2);
-                            }
-                            if (a.out_ssf) {
-                                double *os = a.out_ssf
-                                    + ((c * a.ns + st) * a.M + m) * 3;
-                                os[0] = v0; os[1] = v1; os[2] = v2;
-                            }
+                            double *os = a.out_ssf
+                                + ((c * a.ns + st) * a.M + m) * 3;
+                            os[0] = sp[0]; os[1] = sp[1]; os[2] = sp[2];
                         }
                     }
                     __syncthreads();
                     for (int j = x.I; take && j < VMC_MB && m0 + j < a.M;
                          j += nb) {
                         const int m = m0 + j;
+                        double *sp = S.ssfprev + (c * a.M + m) * 3;
+                        if (flush) {
+                            if (j != x.I) { o0 = sp[0]; o1 = sp[1]; o2 = sp[2]; }
+                            double *ss = a.sum_ssf + (c * a.M + m) * 3;
+                            const double w = (double) nstay;
+                            atomicAdd(ss, w * o0); atomicAdd(ss + 1, w * o1);
+                            atomicAdd(ss + 2, w * o2);
+                        }
                         // two interleaved running sums (fixed order)
                         const double2 *pj = pb + j * nb;
                         double re = 0.0, im = 0.0, re1 = 0.0, im1 = 0.0;
@@ -297,13 +310,7 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                         if (t < nb) { re += pj[t].x; im += pj[t].y; }
                         re += re1; im += im1;
                         const double v0 = fma(re, re, im * im);
-                        double *sp = S.ssfprev + (c * a.M + m) * 3;
                         sp[0] = v0; sp[1] = re; sp[2] = im;
-                        if (a.sum_ssf) {
-                            double *ss = a.sum_ssf + (c * a.M + m) * 3;
-                            atomicAdd(ss, v0); atomicAdd(ss + 1, re);
-                            atomicAdd(ss + 2, im);
-                        }
                         if (a.out_ssf) {
                             double *os = a.out_ssf
                                 + ((c * a.ns + st) * a.M + m) * 3;
@@ -311,11 +318,22 @@ vmc_block_kernel(const __grid_constant__ DevModel M, GroupGeom geom,
                         }
                     }
                 }
+                if (active) nstay = take ? 1 : nstay + 1;
                 // the partials alias the pair tables of the next evaluation
                 __syncthreads();
             }
         }
         if (active) {
+            // the last state's share of the block sums
+            if (a.M > 0 && a.sum_ssf && nstay > 0) {
+                const double w = (double) nstay;
+                for (int m = x.I; m < a.M; m += nb) {
+                    const double *sp = S.ssfprev + (c * a.M + m) * 3;
+                    double *ss = a.sum_ssf + (c * a.M + m) * 3;
+                    atomicAdd(ss, w * sp[0]); atomicAdd(ss + 1, w * sp[1]);
+                    atomicAdd(ss + 2, w * sp[2]);
+                }
+            }
             store4(S.confs + c * 2 * N, x.I, nvalid, vec_ok, z);
             store4(S.confs + c * 2 * N + N, x.I, nvalid, vec_ok, Fcur);
             if (x.I == 0) {
