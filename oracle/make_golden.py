@@ -617,6 +617,10 @@ def main():
         gen_dmc_stat_pure(mrbp, 'lat_n50', SPECS['lat_n50'], n_target=512,
                           wmax=640, dt=1e-3, nts=128, nblocks=160, burn=24,
                           seed=21)
+    if 'statvmc50' in which:
+        # BASELINE configs[1] particle number: one long reference chain
+        gen_vmc_stat(mrbp, 'lat_n50', SPECS['lat_n50'], move_spread=0.25,
+                     ns=4096, nblocks=96, burn=8, seed=3)
     if 'statpure100' in which:
         # BASELINE configs[3] model (N=100, dt of the headline bench)
         # (blocks of tau = 0.16: shorter ones leave the density bins of

@@ -217,7 +217,7 @@ def test_dmc_energy_vs_reference_run(name):
     # (SURVEY.md H1): the reference's semantics are what we match
 
 
-@pytest.mark.parametrize('name', ['ll_n16', 'defects_n20'])
+@pytest.mark.parametrize('name', ['ll_n16', 'defects_n20', 'lat_n50'])
 def test_vmc_energy_and_ssf_vs_reference_run(name):
     """Statistical parity of VMC (north star): energy and <|rho_k|^2> of a
     batch of independent engine chains against one long chain of the LIVE
