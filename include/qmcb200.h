@@ -327,7 +327,10 @@ QMCB_API int qmcb_rebalance_plan(const int64_t *counts, int32_t world,
 
 /* ---- VMC ---------------------------------------------------------------- */
 /* Replaces Sampling.build_state (mrbp_qmc/vmc.py:145-170) for num_chains
- * chains: confs [num_chains][2][N]. */
+ * chains: confs [num_chains][2][N].  Calling it again with the same
+ * num_chains and ssf_num_modes re-initialises the chains in the device
+ * buffers of the previous call (no allocation); page-locked host buffers
+ * make this and the result copies below run at PCIe rate. */
 QMCB_API int qmcb_vmc_init(qmcb_handle *h, const qmcb_vmc_params *params,
                            const double *confs, int64_t num_chains);
 /* Replaces one `next()` of vmc CoreFuncs.blocks (qmc_base/vmc.py:670-770)
