@@ -269,6 +269,62 @@ def test_vmc_config2_n50_chains_vs_oracle(oracle):
         24, 2, 50, 3)
 
 
+def test_vmc_config2_full_size_sums_only(oracle):
+    """BASELINE configs[1] at its full size (1e5 chains, N = 50, M = 50) on
+    the sums-only path the bench times (no per-step series; S(k) block sums
+    accumulated lazily on the device): size-independent identities for every
+    chain, and a slice of chains from the middle of the batch against the
+    oracle (same Philox keys: the chain index is part of the key)."""
+    from phd_qmclib_b200 import engine, model
+    spec = model.Spec(lattice_depth=5 * np.pi ** 2, lattice_ratio=1,
+                      interaction_strength=4, boson_number=50,
+                      supercell_size=50, tbf_contact_cutoff=12.5)
+    p = model.param_block(spec)
+    nop, size, M = 50, 50.0, 50
+    nch, ns, seed = 100000, 48, 9
+    spread = 0.25 * spec.well_width
+    rng = np.random.default_rng(4)
+    ini = np.zeros((nch, 2, nop))
+    ini[:, 0] = (np.arange(nop)[None, :] + 0.25
+                 + 0.15 * (rng.random((nch, nop)) - 0.5))
+    k0, nk = 61234, 40                  # straddles CTA boundaries (G = 19)
+    cur = ini[k0:k0 + nk].copy()
+    ln = oracle.model_eval(p, cur, want=('lnpsi',))['lnpsi']
+    eprev, sprev = np.zeros(nk), np.zeros((nk, M, 3))
+    eng = engine.Engine(spec)
+    eng.vmc_init(ini, spread, seed, 0.0, size, ssf_num_modes=M)
+    step0 = 0
+    for b in range(2):
+        first = b == 0
+        a = oracle.vmc_block(p, seed, spread, 0.0, size, cur, ln, eprev,
+                             sprev, M, ns, step0, first, chain_offset=k0)
+        step0 += ns - (1 if first else 0)
+        o = eng.vmc_run_block(ns, series=False, sums=True)
+        # every step adds |rho_0|^2 = N^2 and rho_0 = N, whatever the moves
+        assert np.array_equal(o['sum_ssf'][:, 0, 0],
+                              np.full(nch, float(ns * nop * nop)))
+        assert np.array_equal(o['sum_ssf'][:, 0, 1],
+                              np.full(nch, float(ns * nop)))
+        assert np.all(o['sum_ssf'][:, 0, 2] == 0.0)
+        assert np.all(o['sum_ssf'][:, :, 0] >= 0.0)
+        assert np.all(np.isfinite(o['sum_energy']))
+        # Cauchy-Schwarz of the two energy sums
+        assert np.all(o['sum_energy'][:, 0] ** 2
+                      <= ns * o['sum_energy'][:, 1] * (1 + 1e-12))
+        assert 0.3 < o['accept_rate'].mean() < 0.7
+        sl = slice(k0, k0 + nk)
+        assert np.allclose(o['accept_rate'][sl], a['accept_rate'], rtol=0,
+                           atol=1e-15)
+        assert np.allclose(o['sum_energy'][sl, 0], a['energy'].sum(axis=1),
+                           rtol=1e-11)
+        assert np.allclose(o['sum_ssf'][sl], a['ssf'].sum(axis=1), rtol=1e-9,
+                           atol=1e-7)
+    confs, lnpsi = eng.vmc_get_state()
+    assert np.allclose(confs[k0:k0 + nk, 0], cur[:, 0], rtol=0, atol=1e-12)
+    assert rel_err(lnpsi[k0:k0 + nk], ln) < 1e-11
+    eng.close()
+
+
 @pytest.mark.parametrize('energy_mode', [0, 1])
 def test_sharded_code_path_on_one_rank_vs_oracle(oracle, energy_mode):
     """The multi-rank machinery on a communicator of ONE rank (what a
