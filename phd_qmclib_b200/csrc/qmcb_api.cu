@@ -382,6 +382,26 @@ bool choose_geom(const DevModel &M, int max_smem, GroupGeom &g,
     return true;
 }
 
+// Kernel launch, optionally as a programmatic dependent of the kernel before
+// it in the stream (cudaLaunchAttributeProgrammaticStreamSerialization).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block,
+                       size_t smem, cudaStream_t stream, bool pdl,
+                       Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <typename K>
 int set_smem(qmcb_handle *h, K kernel)
 {
@@ -1476,10 +1496,16 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
     const bool use_graph = !no_graph && !h->comm && !h->profile_steps
                            && !do_ssf && !do_den;
     const bool step_fast = step_fast_ok(h);
+    // programmatic dependent launch between the kernels of a time step (see
+    // pdl_enter); one rank only: with a communicator the NCCL kernels and
+    // the second stream sit between them
+    static const bool no_pdl = getenv("QMCB_NO_PDL") != nullptr;
+    const bool pdl = !no_pdl && !h->comm;
     auto enqueue_step = [&](int64_t i) -> int {
         const int fuse = (glob_a && h->weights_pending) ? 1 : 0;
-        branch_count_kernel<<<B.nblk, BR_THREADS, 0, h->stream>>>(B, h->C, X,
-                                                                  fuse);
+        CUDA_TRY(h, launch_pdl(branch_count_kernel, dim3(B.nblk),
+                               dim3(BR_THREADS), 0, h->stream, pdl, B, h->C,
+                               X, fuse));
         if (fuse) {
             // the previous step's update of the global array: after its
             // values have been read above, off the critical path
@@ -1487,8 +1513,9 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
             CUDA_TRY(h, cudaStreamWaitEvent(h->pc_stream, h->ev_weighted, 0));
             multi_apply_kernel<<<h->sm_count * 4, 256, 0, h->pc_stream>>>(X);
         }
-        branch_fill_kernel<<<B.nblk, BR_THREADS, 0, h->stream>>>(
-            B, h->C, L, h->comm ? 0 : 1);
+        CUDA_TRY(h, launch_pdl(branch_fill_kernel, dim3(B.nblk),
+                               dim3(BR_THREADS), 0, h->stream, pdl, B, h->C,
+                               L, h->comm ? 0 : 1));
         if (h->comm) {
             // Population control needs the GLOBAL {sum E, W}
             // (qmc_base/dmc.py:758-771) and, with the reference's stale-slot
@@ -1517,11 +1544,13 @@ int qmcb_dmc_run_block(qmcb_handle *h, int64_t nts, int32_t eval_estimators,
         if (h->profile_steps)
             CUDA_TRY(h, cudaEventRecord(h->step_ev[2 * i], h->stream));
         if (step_fast)
-            dmc_step_kernel<true><<<step_grid, g.nthreads, g.smem_bytes,
-                                    h->stream>>>(h->M, g, B, h->C);
+            CUDA_TRY(h, launch_pdl(dmc_step_kernel<true>, dim3(step_grid),
+                                   dim3(g.nthreads), (size_t) g.smem_bytes,
+                                   h->stream, pdl, h->M, g, B, h->C));
         else
-            dmc_step_kernel<false><<<step_grid, g.nthreads, g.smem_bytes,
-                                     h->stream>>>(h->M, g, B, h->C);
+            CUDA_TRY(h, launch_pdl(dmc_step_kernel<false>, dim3(step_grid),
+                                   dim3(g.nthreads), (size_t) g.smem_bytes,
+                                   h->stream, pdl, h->M, g, B, h->C));
         if (h->profile_steps)
             CUDA_TRY(h, cudaEventRecord(h->step_ev[2 * i + 1], h->stream));
         if (h->comm) {

@@ -268,6 +268,20 @@ __device__ __forceinline__ void branch_scan_blocks(const DmcBufs &B)
     }
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may become resident
+// while its predecessor in the stream is still running.  Every such kernel
+// first waits here for the predecessor's COMPLETION (all its memory
+// operations visible), then lets its own successor in: the launch latency
+// and the CTA scheduling of the three kernels of a DMC time step overlap
+// the tail of the kernel before.  Without the launch attribute both calls
+// return at once.
+__device__ __forceinline__ void pdl_enter()
+{
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+}
+
 // True in exactly one CTA of the grid: the last one to get here.  Its reads
 // (through __ldcg) see everything the other CTAs wrote before their call.
 __device__ __forceinline__ bool last_cta_done(unsigned int *counter)
@@ -290,6 +304,7 @@ __device__ __forceinline__ bool last_cta_done(unsigned int *counter)
 __global__ void __launch_bounds__(BR_THREADS)
 branch_count_kernel(DmcBufs B, DmcConsts C, DmcMulti X, int fuse_weight)
 {
+    pdl_enter();
     const DmcCtl *ctl = B.ctl;
     const int Wp = ctl->W_prev;
     const int par = (int) (ctl->step & 1);
@@ -378,6 +393,7 @@ __device__ __forceinline__ void dmc_finalize(const DmcBufs &B,
 __global__ void __launch_bounds__(BR_THREADS)
 branch_fill_kernel(DmcBufs B, DmcConsts C, DmcLog L, int finalize)
 {
+    pdl_enter();
     const DmcCtl *ctl = B.ctl;
     const int par = (int) (ctl->step & 1);
     const double *e = B.energy[par];
@@ -531,6 +547,7 @@ __global__ void __launch_bounds__(QMCB_STEP_THREADS, QMCB_STEP_MINCTAS)
 dmc_step_kernel(const __grid_constant__ DevModel M, GroupGeom geom, DmcBufs B,
                 DmcConsts C)
 {
+    pdl_enter();
     const DmcCtl *ctl = B.ctl;
     const int W = ctl->W;
     const long long s0 = (long long) blockIdx.x * geom.G;
