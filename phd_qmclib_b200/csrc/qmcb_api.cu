@@ -459,7 +459,7 @@ void free_dmc(qmcb_handle *h)
         cudaFree(B.confs[i]); cudaFree(B.energy[i]); cudaFree(B.weight[i]);
     }
     cudaFree(B.slot_energy); cudaFree(B.ref); cudaFree(B.cnt);
-    cudaFree(B.blocksum); cudaFree(B.blockoff); cudaFree(B.epart);
+    cudaFree(B.blocksum); cudaFree(B.epart);
     cudaFree(B.ctl);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->ssf_aux[i]); cudaFree(h->den_hist[i]);
@@ -532,7 +532,6 @@ int alloc_dmc(qmcb_handle *h, const qmcb_dmc_params *p,
         CUDA_TRY(h, cudaMalloc(&B.ref, cap * sizeof(int)));
         CUDA_TRY(h, cudaMalloc(&B.cnt, cap * sizeof(int)));
         CUDA_TRY(h, cudaMalloc(&B.blocksum, B.nblk * sizeof(long long)));
-        CUDA_TRY(h, cudaMalloc(&B.blockoff, B.nblk * sizeof(long long)));
         CUDA_TRY(h, cudaMalloc(&B.epart, B.nblk * sizeof(double)));
         CUDA_TRY(h, cudaMalloc(&B.ctl, sizeof(DmcCtl)));
         for (int i = 0; i < 2; ++i)

@@ -144,7 +144,6 @@ struct DmcCtl {
     double red[2];              // {sum E_parents, W}: local, then global
     double last_energy, last_weight, last_accum;
     double W_global;            // global live walkers of the last step
-    unsigned int done_count;    // CTAs of branch_count_kernel that finished
     unsigned int done_fill;     // CTAs of branch_fill_kernel that finished
     long long block_step0;      // `step` at the start of the block in flight
     long long tcur;             // time step the step kernel in flight works
@@ -166,7 +165,6 @@ struct DmcBufs {
     int *ref;                   // [cap]  child slot -> parent slot
     int *cnt;                   // [cap]  clone counts
     long long *blocksum;        // [nblk]
-    long long *blockoff;        // [nblk]
     double *epart;              // [nblk]
     DmcCtl *ctl;
     int cap;
@@ -242,32 +240,6 @@ __device__ __forceinline__ long long block_excl_scan(long long v,
     return r;
 }
 
-// Scan of the per-CTA sums (one CTA); fixes W for this step.
-__device__ __forceinline__ void branch_scan_blocks(const DmcBufs &B)
-{
-    __shared__ long long carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int b0 = 0; b0 < B.nblk; b0 += BR_THREADS) {
-        int b = b0 + threadIdx.x;
-        long long v = (b < B.nblk) ? __ldcg(B.blocksum + b) : 0;
-        long long tot;
-        long long ex = block_excl_scan(v, &tot);
-        long long carry = carry_s;
-        if (b < B.nblk) B.blockoff[b] = carry + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + tot;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        DmcCtl *ctl = B.ctl;
-        long long total = carry_s;
-        ctl->total_children = total;
-        if (total > B.cap) { ctl->capacity_hits += 1; total = B.cap; }
-        ctl->W = (int) total;
-    }
-}
-
 // Programmatic dependent launch (sm_90+): a kernel launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization may become resident
 // while its predecessor in the stream is still running.  Every such kernel
@@ -299,8 +271,8 @@ __device__ __forceinline__ bool last_cta_done(unsigned int *counter)
     return is_last;
 }
 
-// K4a+b: clone counts c_s = int(w_s + u_s) (qmc_base/dmc.py:641-643) and, in
-// the last CTA to finish, the scan of the per-CTA sums.
+// K4a: clone counts c_s = int(w_s + u_s) (qmc_base/dmc.py:641-643) and their
+// per-CTA totals.
 __global__ void __launch_bounds__(BR_THREADS)
 branch_count_kernel(DmcBufs B, DmcConsts C, DmcMulti X, int fuse_weight)
 {
@@ -347,7 +319,6 @@ branch_count_kernel(DmcBufs B, DmcConsts C, DmcMulti X, int fuse_weight)
     long long tot;
     block_excl_scan(local, &tot);
     if (threadIdx.x == 0) B.blocksum[blockIdx.x] = tot;
-    if (last_cta_done(&B.ctl->done_count)) branch_scan_blocks(B);
 }
 
 // K7: population control (qmc_base/dmc.py:758-771) from the (global) sums in
@@ -406,7 +377,15 @@ branch_fill_kernel(DmcBufs B, DmcConsts C, DmcLog L, int finalize)
         c[i] = (s < B.cap) ? B.cnt[s] : 0;
         local += c[i];
     }
-    long long off = block_excl_scan(local, nullptr) + B.blockoff[blockIdx.x];
+    // children of the CTAs before this one: every CTA adds up the per-CTA
+    // totals itself (a few hundred values at most; saves the scan pass and
+    // its grid-wide hand-over in branch_count_kernel)
+    long long before = 0;
+    for (int b = threadIdx.x; b < (int) blockIdx.x; b += BR_THREADS)
+        before += B.blocksum[b];
+    long long boff;
+    block_excl_scan(before, &boff);
+    long long off = block_excl_scan(local, nullptr) + boff;
     double esum = 0.0;
 #pragma unroll
     for (int i = 0; i < BR_ITEMS; ++i) {
@@ -431,6 +410,18 @@ branch_fill_kernel(DmcBufs B, DmcConsts C, DmcLog L, int finalize)
     }
     if (threadIdx.x == 0) B.epart[blockIdx.x] = red[0];
     if (!last_cta_done(&B.ctl->done_fill)) return;
+    // W of this step: all children, truncated at the capacity
+    long long kids = 0;
+    for (int b = threadIdx.x; b < B.nblk; b += BR_THREADS)
+        kids += B.blocksum[b];
+    long long total;
+    block_excl_scan(kids, &total);
+    if (threadIdx.x == 0) {
+        DmcCtl *c = B.ctl;
+        c->total_children = total;
+        if (total > B.cap) { c->capacity_hits += 1; total = B.cap; }
+        c->W = (int) total;
+    }
     double acc = 0.0;
     for (int b = threadIdx.x; b < B.nblk; b += BR_THREADS)
         acc += __ldcg(B.epart + b);
