@@ -1,7 +1,7 @@
 """GPU parity at the populations the bench runs: capacities far beyond one
 branching tile (BR_TILE = 1024 slots), so that the multi-CTA form of
-`sync_branching_spec` (qmc_base/dmc.py:614-655) -- per-CTA counts, the scan of
-the CTA sums by the last CTA to finish, the block-offset carry, the truncation
+`sync_branching_spec` (qmc_base/dmc.py:614-655) -- per-CTA counts, the offset
+of a CTA from the totals of the CTAs before it, the truncation
 at capacity across CTA boundaries and the fixed-order sum of the cloned
 parents' energies (state_energy, qmc_base/dmc.py:759-760) -- is compared with
 the serial oracle on the same Philox streams.  Bit-equal walker counts and
