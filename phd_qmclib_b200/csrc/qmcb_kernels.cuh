@@ -240,6 +240,26 @@ __device__ __forceinline__ long long block_excl_scan(long long v,
     return r;
 }
 
+// Sum of one value per thread over a BR_THREADS CTA, on every thread: warp
+// shuffles, then the warp totals.  The tree has a fixed shape, so the
+// floating-point result does not depend on scheduling.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v)
+{
+    __shared__ T part[BR_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        v += __shfl_down_sync(0xffffffffu, v, d);
+    if (lane == 0) part[wid] = v;
+    __syncthreads();
+    T r = part[0];
+#pragma unroll
+    for (int w = 1; w < BR_THREADS / 32; ++w) r += part[w];
+    __syncthreads();            // part may be written again
+    return r;
+}
+
 // Programmatic dependent launch (sm_90+): a kernel launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization may become resident
 // while its predecessor in the stream is still running.  Every such kernel
@@ -316,8 +336,7 @@ branch_count_kernel(DmcBufs B, DmcConsts C, DmcMulti X, int fuse_weight)
         if (s < B.cap) B.cnt[s] = c;
         local += c;
     }
-    long long tot;
-    block_excl_scan(local, &tot);
+    const long long tot = block_sum(local);
     if (threadIdx.x == 0) B.blocksum[blockIdx.x] = tot;
 }
 
@@ -383,8 +402,7 @@ branch_fill_kernel(DmcBufs B, DmcConsts C, DmcLog L, int finalize)
     long long before = 0;
     for (int b = threadIdx.x; b < (int) blockIdx.x; b += BR_THREADS)
         before += B.blocksum[b];
-    long long boff;
-    block_excl_scan(before, &boff);
+    const long long boff = block_sum(before);
     long long off = block_excl_scan(local, nullptr) + boff;
     double esum = 0.0;
 #pragma unroll
@@ -401,39 +419,24 @@ branch_fill_kernel(DmcBufs B, DmcConsts C, DmcLog L, int finalize)
         off += c[i];
     }
     // fixed-shape CTA reduction: deterministic
-    __shared__ double red[BR_THREADS];
-    red[threadIdx.x] = esum;
-    __syncthreads();
-    for (int d = BR_THREADS / 2; d > 0; d >>= 1) {
-        if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) B.epart[blockIdx.x] = red[0];
+    const double epart = block_sum(esum);
+    if (threadIdx.x == 0) B.epart[blockIdx.x] = epart;
     if (!last_cta_done(&B.ctl->done_fill)) return;
     // W of this step: all children, truncated at the capacity
     long long kids = 0;
-    for (int b = threadIdx.x; b < B.nblk; b += BR_THREADS)
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < B.nblk; b += BR_THREADS) {
         kids += B.blocksum[b];
-    long long total;
-    block_excl_scan(kids, &total);
+        acc += __ldcg(B.epart + b);
+    }
+    long long total = block_sum(kids);
+    const double etot = block_sum(acc);
     if (threadIdx.x == 0) {
         DmcCtl *c = B.ctl;
         c->total_children = total;
         if (total > B.cap) { c->capacity_hits += 1; total = B.cap; }
         c->W = (int) total;
-    }
-    double acc = 0.0;
-    for (int b = threadIdx.x; b < B.nblk; b += BR_THREADS)
-        acc += __ldcg(B.epart + b);
-    __syncthreads();
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int d = BR_THREADS / 2; d > 0; d >>= 1) {
-        if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        B.ctl->red[0] = red[0];
+        B.ctl->red[0] = etot;
         B.ctl->red[1] = (double) B.ctl->W;
         B.ctl->tcur = B.ctl->step;
         if (finalize) dmc_finalize(B, C, L);
