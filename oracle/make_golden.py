@@ -6,7 +6,13 @@ fixtures to ``tests/golden/``.  The reference's own tests hold no golden
 vectors for this path, so these files are the pin for
 both the C oracle and the CUDA engine.
 
-    python oracle/make_golden.py            # regenerate everything
+    python oracle/make_golden.py            # the deterministic fixtures and
+                                            # the N=16/20 statistical runs
+    python oracle/make_golden.py statpure statpure100 statpure200 statvmc50
+                                            # the long runs at the BASELINE
+                                            # particle numbers (N = 50, 100,
+                                            # 200 DMC with the pure estimators,
+                                            # N = 50 VMC): minutes each
 
 Every random input is drawn from a seeded numpy Generator; every random
 number the reference consumes *inside* its JIT code is re-drawn afterwards
